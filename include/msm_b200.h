@@ -1,0 +1,177 @@
+/* msm_b200.h -- C ABI of libmsm_b200.so, the B200-native MSM engine.
+ *
+ * Drop-in boundary for the reference's MSM entry points (scalars + affine points in, one curve
+ * point out).  Every entry point names the reference interface it replaces (paths relative to
+ * the reference repo).  Plain pointers and sizes only; no C++/torch types.  All functions return
+ * 0 on success or a negative MSM_E_* code; msm_b200_last_error() gives a message.  Nothing here
+ * throws or aborts across the ABI (the reference's JS exceptions / wasm traps become codes).
+ *
+ * One context = one GPU + one curve.  A context is single-caller (not re-entrant), like one
+ * thread-pool instance of the reference (src/threads/threads.ts:132-277).
+ */
+#ifndef MSM_B200_H
+#define MSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msm_b200_ctx msm_b200_ctx;
+
+/* curves: src/concrete/bls12-377.params.ts, pasta.params.ts, ed-on-bls12-377.params.ts */
+enum msm_b200_curve {
+  MSM_CURVE_BLS12_377_G1 = 0, /* short Weierstrass a=0, GLV, 377-bit base field */
+  MSM_CURVE_PALLAS = 1,       /* short Weierstrass a=0, GLV, 255-bit base field */
+  MSM_CURVE_ED_ON_BLS12_377 = 2 /* twisted Edwards a=-1, 253-bit base field */
+};
+
+/* algorithm ("form"): which of the reference's MSMs the call mirrors */
+enum msm_b200_form {
+  MSM_FORM_AFFINE_GLV = 0, /* createMsm().msm / msmUnsafe, src/msm-batched-affine.ts:74-328,573-587 */
+  MSM_FORM_PROJECTIVE = 1, /* Parallel.msmProjective -> msmBasic, src/parallel.ts:69-87, src/msm-basic.ts:45-176 */
+  MSM_FORM_TE_EXTENDED = 2 /* TwistedEdwards Parallel.msm -> msmBasic, src/parallel.ts:193-199 */
+};
+
+/* data layouts at the boundary */
+enum msm_b200_layout {
+  /* The reference's in-memory (wasm) format.  Points: src/curve-affine.ts:20-52 (x | y | u8
+   * isNonZero + 3 pad; 2*4*n+4 bytes, n = 14 or 9 limbs of 29 bits in u32 words, Montgomery
+   * R = 2^(29n), coordinates may be unreduced in [0,2p)); twisted Edwards: X|Y|Z|T, 4*4*n bytes,
+   * Z = R mod p (src/curve-twisted-edwards.ts:30-31).  Scalars: 9 x 29-bit limbs in u32 words,
+   * plain integers < q (src/scalar-glv.ts:60-66). */
+  MSM_LAYOUT_LIMB29_MONT = 0,
+  /* The compute_msm wire format: canonical little-endian bytes.  Points x|y, 48|48 bytes
+   * (BLS12-377) or 32|32 (Pallas, ed-on-bls12-377): src/parallel.ts:97-116,209-232.
+   * Scalars 32 bytes LE: src/parallel.ts:119-133.  No representation of the zero point
+   * (src/parallel.ts:107-108). */
+  MSM_LAYOUT_LE_BYTES = 1
+};
+
+enum msm_b200_error {
+  MSM_OK = 0,
+  MSM_E_INVALID = -1, /* bad argument (replaces `assert`, src/util.ts:256) */
+  MSM_E_CUDA = -2,    /* CUDA runtime failure, incl. no device */
+  MSM_E_NOMEM = -3,   /* device allocation failed (replaces the memory-overflow exception,
+                         src/wasm/memory-helpers.ts:224-236) */
+  MSM_E_STATE = -4    /* call order (e.g. run before set_bases) */
+};
+
+/* Per-phase timings in milliseconds (CUDA events), the analogue of the reference's tic/toc log
+ * (src/msm-common.ts:192-230) returned by msm(..., verboseTiming=true). */
+typedef struct msm_b200_timing {
+  float h2d_ms;       /* scalars (and points, for the one-shot call) host -> device */
+  float ingest_ms;    /* layout conversion: "prepare points & scalars" */
+  float digits_ms;    /* GLV decompose + signed digits + histogram: "slice scalars & count buckets" */
+  float sort_ms;      /* offsets + scatter: "integrate bucket counts", "sort points" */
+  float accumulate_ms;/* "bucket accumulation" */
+  float reduce_ms;    /* "bucket reduction", "partition sum", "final sum" + normalisation */
+  float d2h_ms;
+  float total_ms;     /* whole call, host clock */
+  /* dominant kernel (batched-affine backward pass / bucket accumulate) */
+  float hot_kernel_ms;      /* sum of its launch durations in this call */
+  int hot_kernel_launches;
+  int kernel_launches;      /* all kernels launched by this call */
+  int window_bits;          /* c actually used */
+  int n_windows;            /* K */
+  int rounds;               /* batched-affine tree rounds */
+  unsigned long long n_adds;/* point additions performed in the accumulation */
+} msm_b200_timing;
+
+/* Result point, canonical affine (the normalisation that defines parity: Projective.toAffine +
+ * Affine.toBigint, src/curve-projective.ts:335-349, src/curve-affine.ts:220-233; twisted Edwards:
+ * src/curve-twisted-edwards.ts:369-386).  x, y little-endian, 48 bytes used for BLS12-377, 32
+ * for the others (rest zero).  is_zero: Weierstrass point at infinity (x = y = 0 then); the
+ * twisted-Edwards zero is the ordinary point (0, 1) with is_zero = 1 as a convenience. */
+typedef struct msm_b200_point {
+  uint8_t x[48];
+  uint8_t y[48];
+  int32_t is_zero;
+} msm_b200_point;
+
+/* -- lifecycle ------------------------------------------------------------------------------
+ * replaces Weierstrass.create / TwistedEdwards.create + startThreads (src/parallel.ts:40-177,
+ * 179-289, 291-315): builds the per-curve engine on CUDA device `device`.
+ * `stream`: a cudaStream_t to run on (e.g. torch's current stream), or NULL for an own stream. */
+int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream);
+/* replaces stopThreads (src/parallel.ts:317-320) */
+void msm_b200_destroy(msm_b200_ctx* ctx);
+const char* msm_b200_last_error(const msm_b200_ctx* ctx);
+/* library-level message for failures before a context exists */
+const char* msm_b200_global_error(void);
+
+/* -- inputs ---------------------------------------------------------------------------------
+ * Uploads and prepares the point set (kept resident, like points living in wasm memory across
+ * benchmark iterations, scripts/msm-weierstrass.ts:19,29-33).  Does on the device what
+ * preparePointsAndScalars does per point (copy, endomorphism; src/msm-batched-affine.ts:338-409)
+ * and, for LE_BYTES, what Parallel.pointsFromBytes does (src/parallel.ts:97-116,209-232).
+ * `points` is host memory unless `on_device` != 0. */
+int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device);
+
+/* -- the MSM --------------------------------------------------------------------------------
+ * replaces Parallel.msm / Parallel.msmUnsafe / Parallel.msmProjective
+ * (src/msm-batched-affine.ts:74-83,573-587; src/parallel.ts:69-87; src/msm-basic.ts:34-43) over
+ * the resident bases: sum_i scalars[i] * bases[i], i < n <= n_bases.
+ * `window_bits`: the reference's options.c (0 = engine default).  `form`: msm_b200_form.
+ * `scalars` is host memory unless `on_device` != 0.  `timing` may be NULL. */
+int msm_b200_run(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_layout, int on_device,
+                 int form, int window_bits, msm_b200_point* out, msm_b200_timing* timing);
+
+/* One-shot call with host buffers for both inputs: set_bases + run, the shape of
+ * compute_msm(points, scalars) (scripts/zprize23/submission-bls377.ts:20-65, submission.ts:19-35)
+ * and of a cold Parallel.msm call. */
+int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, const void* points,
+                 int point_layout, size_t n, int form, int window_bits, msm_b200_point* out,
+                 msm_b200_timing* timing);
+
+/* Same as msm_b200_run but leaves the result on the device: writes one partial (internal
+ * representation, msm_b200_partial_bytes() bytes) to `partial_dev` (device memory, e.g. a torch
+ * tensor that is then all-gathered with NCCL).  Multi-GPU: each rank owns a contiguous point
+ * range (the GPU analogue of range(), src/threads/threads.ts:354-359). */
+int msm_b200_run_partial(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_layout,
+                         int on_device, int form, int window_bits, void* partial_dev,
+                         msm_b200_timing* timing);
+size_t msm_b200_partial_bytes(const msm_b200_ctx* ctx);
+/* Adds `count` gathered partials (device memory) and normalises: the "partition sum / final sum"
+ * of src/msm-batched-affine.ts:299-322 across GPUs. */
+int msm_b200_combine(msm_b200_ctx* ctx, const void* partials_dev, int count, msm_b200_point* out);
+
+/* -- synthetic inputs on the device ----------------------------------------------------------
+ * replaces Parallel.randomPointsFast / randomScalars (src/curve-random.ts:24-91,151-194) with
+ * seeded generators (the reference has no seeds, src/util.ts:226-233): writes `n` points /
+ * scalars in LE_BYTES layout into device memory `dst_dev` (n * point_bytes / n * 32 bytes). */
+int msm_b200_random_points(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed);
+int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed);
+size_t msm_b200_point_bytes(const msm_b200_ctx* ctx, int layout);
+size_t msm_b200_scalar_bytes(const msm_b200_ctx* ctx, int layout);
+
+/* -- device memory helpers for hosts without a CUDA binding (the N-API addon) ---------------- */
+int msm_b200_dev_alloc(msm_b200_ctx* ctx, void** out_dev, size_t bytes);
+int msm_b200_dev_free(msm_b200_ctx* ctx, void* dev);
+int msm_b200_host_alloc_pinned(void** out_host, size_t bytes);
+int msm_b200_host_free_pinned(void* host);
+int msm_b200_memcpy_d2h(msm_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+
+/* -- test / measurement hooks ----------------------------------------------------------------
+ * Field ops on the device, element-wise over `n` elements (32-bit limbs, internal Montgomery
+ * form) -- the device side of the reference's per-op tests (src/field.test.ts:15-155).
+ * field: 0 BLS12-377 Fq, 1 Pallas Fp, 2 BLS12-377 Fr.  op: 0 mul, 1 add, 2 sub, 3 inverse. */
+int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host,
+                           const uint32_t* b_host, uint32_t* out_host, size_t n);
+/* GLV decomposition + signed digits on the device for `n` scalars (LE_BYTES): writes
+ * 2n * K digits as u32 (bucket l | sign << 31), half-scalar major.  (src/glv/glv-test.ts,
+ * src/msm-batched-affine.ts:172-200) */
+int msm_b200_test_digits(msm_b200_ctx* ctx, const void* scalars_host, size_t n, int window_bits,
+                         uint32_t* digits_host, int* n_windows);
+/* Integer-pipe micro-benchmarks: which = 0 IMAD (mad.lo), 1 IMAD.WIDE (mad.wide.u32),
+ * 2 mad.lo.cc/madc.hi.cc carry chain, 3 Montgomery product 12 limbs, 4 Montgomery product 8 limbs,
+ * 5 IMAD.HI.  Returns operations per second (limb products for 0-2 and 5, modmuls for 3-4). */
+int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSM_B200_H */

@@ -1,0 +1,104 @@
+"""ctypes binding of libmsm_b200.so (the C ABI declared in include/msm_b200.h).
+
+This is the tested stand-in for the N-API addon the reference's TypeScript host would load
+(INTEGRATION.md): same entry points, same argument meaning.  There is no CPU fallback: if the
+CUDA library is missing or no GPU is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmsm_b200.so")
+
+# enums (include/msm_b200.h)
+CURVE_BLS12_377_G1, CURVE_PALLAS, CURVE_ED_ON_BLS12_377 = 0, 1, 2
+FORM_AFFINE_GLV, FORM_PROJECTIVE, FORM_TE_EXTENDED = 0, 1, 2
+LAYOUT_LIMB29_MONT, LAYOUT_LE_BYTES = 0, 1
+E_INVALID, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float), ("ingest_ms", C.c_float), ("digits_ms", C.c_float),
+        ("sort_ms", C.c_float), ("accumulate_ms", C.c_float), ("reduce_ms", C.c_float),
+        ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("hot_kernel_ms", C.c_float),
+        ("hot_kernel_launches", C.c_int), ("kernel_launches", C.c_int), ("window_bits", C.c_int),
+        ("n_windows", C.c_int), ("rounds", C.c_int), ("n_adds", C.c_ulonglong),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Point(C.Structure):
+    _fields_ = [("x", C.c_uint8 * 48), ("y", C.c_uint8 * 48), ("is_zero", C.c_int32)]
+
+
+class MsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"msm_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+EXPORTS = [
+    "msm_b200_create", "msm_b200_destroy", "msm_b200_last_error", "msm_b200_global_error",
+    "msm_b200_set_bases", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial",
+    "msm_b200_partial_bytes", "msm_b200_combine", "msm_b200_random_points",
+    "msm_b200_random_scalars", "msm_b200_point_bytes", "msm_b200_scalar_bytes",
+    "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
+    "msm_b200_host_free_pinned", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
+    "msm_b200_test_field_op", "msm_b200_test_digits", "msm_b200_microbench",
+]
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises loudly if it has not been built (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MsmError(E_CUDA, f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    L.msm_b200_create.argtypes = [C.POINTER(vp), ci, ci, vp]
+    L.msm_b200_destroy.argtypes = [vp]
+    L.msm_b200_destroy.restype = None
+    L.msm_b200_last_error.argtypes = [vp]
+    L.msm_b200_last_error.restype = C.c_char_p
+    L.msm_b200_global_error.restype = C.c_char_p
+    L.msm_b200_set_bases.argtypes = [vp, vp, sz, ci, ci]
+    L.msm_b200_run.argtypes = [vp, vp, sz, ci, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
+    L.msm_b200_msm.argtypes = [vp, vp, ci, vp, ci, sz, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
+    L.msm_b200_run_partial.argtypes = [vp, vp, sz, ci, ci, ci, ci, vp, C.POINTER(Timing)]
+    L.msm_b200_partial_bytes.argtypes = [vp]
+    L.msm_b200_partial_bytes.restype = sz
+    L.msm_b200_combine.argtypes = [vp, vp, ci, C.POINTER(Point)]
+    L.msm_b200_random_points.argtypes = [vp, vp, sz, C.c_uint64]
+    L.msm_b200_random_scalars.argtypes = [vp, vp, sz, C.c_uint64]
+    L.msm_b200_point_bytes.argtypes = [vp, ci]
+    L.msm_b200_point_bytes.restype = sz
+    L.msm_b200_scalar_bytes.argtypes = [vp, ci]
+    L.msm_b200_scalar_bytes.restype = sz
+    L.msm_b200_dev_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.msm_b200_dev_free.argtypes = [vp, vp]
+    L.msm_b200_host_alloc_pinned.argtypes = [C.POINTER(vp), sz]
+    L.msm_b200_host_free_pinned.argtypes = [vp]
+    L.msm_b200_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.msm_b200_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.msm_b200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
+    L.msm_b200_test_digits.argtypes = [vp, vp, sz, ci, vp, C.POINTER(ci)]
+    L.msm_b200_microbench.argtypes = [ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def check(rc: int, ctx=None):
+    if rc == 0:
+        return
+    L = lib()
+    msg = (L.msm_b200_last_error(ctx) if ctx else L.msm_b200_global_error()) or b""
+    raise MsmError(rc, msg.decode("utf-8", "replace"))

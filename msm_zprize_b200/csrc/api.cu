@@ -1,0 +1,383 @@
+// libmsm_b200.so -- the C ABI (include/msm_b200.h) over the per-curve engines.
+#include "engine.cuh"
+#include "microbench.cuh"
+
+std::string& msm_global_err() {
+  static thread_local std::string e;
+  return e;
+}
+
+static const CurveOps* ops_of(int curve) {
+  switch (curve) {
+    case MSM_CURVE_BLS12_377_G1: return curve_ops_bls377();
+    case MSM_CURVE_PALLAS: return curve_ops_pallas();
+    case MSM_CURVE_ED_ON_BLS12_377: return curve_ops_ed377();
+  }
+  return nullptr;
+}
+
+static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device) {
+  if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
+  if (layout != MSM_LAYOUT_LIMB29_MONT && layout != MSM_LAYOUT_LE_BYTES) return fail(ctx, MSM_E_INVALID, "bad point layout");
+  if (n == 0 || !points) {
+    ctx->n_bases = 0;
+    return n == 0 ? 0 : fail(ctx, MSM_E_INVALID, "null points");
+  }
+  if (n > ((size_t)1 << 30)) return fail(ctx, MSM_E_INVALID, "too many points (max 2^30)");
+  CK(cudaSetDevice(ctx->device));
+  const void* d_in = points;
+  if (!on_device) {
+    size_t bytes = n * point_bytes(ctx->curve, layout);
+    RET_IF(ensure(ctx, ctx->raw_points, bytes));
+    CK(cudaMemcpyAsync(ctx->raw_points.p, points, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = ctx->raw_points.p;
+  }
+  RET_IF(ops_of(ctx->curve)->ingest(ctx, d_in, n, layout));
+  ctx->n_bases = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// run: scalars -> partial (device)
+// ------------------------------------------------------------------------------------------
+static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, int layout, int on_device, int form,
+                            int window_bits, msm_b200_timing* tm, uint32_t* digits_dump_dev = nullptr) {
+  if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
+  if (layout != MSM_LAYOUT_LIMB29_MONT && layout != MSM_LAYOUT_LE_BYTES) return fail(ctx, MSM_E_INVALID, "bad scalar layout");
+  if (n > ctx->n_bases) return fail(ctx, MSM_E_STATE, "more scalars than resident bases (call set_bases first)");
+  if (n > 0 && !scalars) return fail(ctx, MSM_E_INVALID, "null scalars");
+  const bool te = ctx->curve == MSM_CURVE_ED_ON_BLS12_377;
+  if (te && form != MSM_FORM_TE_EXTENDED) return fail(ctx, MSM_E_INVALID, "twisted Edwards curve needs MSM_FORM_TE_EXTENDED");
+  if (!te && form != MSM_FORM_AFFINE_GLV && form != MSM_FORM_PROJECTIVE)
+    return fail(ctx, MSM_E_INVALID, "Weierstrass curve needs MSM_FORM_AFFINE_GLV or MSM_FORM_PROJECTIVE");
+  CK(cudaSetDevice(ctx->device));
+  int c = window_bits > 0 ? window_bits : default_window(ctx->curve, form, n ? n : 1);
+  if (c < 1 || c > 24) return fail(ctx, MSM_E_INVALID, "window_bits out of range [1,24]");
+  Timer T(ctx);
+  int t0 = T.mark();
+  const void* d_s = scalars;
+  if (!on_device && n) {
+    size_t bytes = n * scalar_bytes(layout);
+    RET_IF(ensure(ctx, ctx->raw_scalars, bytes));
+    CK(cudaMemcpyAsync(ctx->raw_scalars.p, scalars, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_s = ctx->raw_scalars.p;
+  }
+  int t1 = T.mark();
+  if (tm) {
+    memset(tm, 0, sizeof *tm);
+  }
+  int rc;
+  if (n == 0)
+    rc = ops_of(ctx->curve)->zero_partial(ctx);
+  else
+    rc = ops_of(ctx->curve)->run(ctx, d_s, n, layout, form, c, tm, digits_dump_dev);
+  RET_IF(rc);
+  if (tm) {
+    tm->h2d_ms = T.ms(t0, t1);
+    tm->kernel_launches = ctx->launches;
+  }
+  return 0;
+}
+
+static size_t partial_bytes(int curve) {
+  return (curve == MSM_CURVE_ED_ON_BLS12_377 ? 4 : 3) * (size_t)field_limbs(curve) * 4;
+}
+
+static int combine_impl(msm_b200_ctx* ctx, const void* partials_dev, int count, msm_b200_point* out) {
+  if (!ctx || !out || count < 1) return fail(ctx, MSM_E_INVALID, "bad combine arguments");
+  CK(cudaSetDevice(ctx->device));
+  return ops_of(ctx->curve)->finalize(ctx, partials_dev, count, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_test_field(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<F> x, y, r;
+  for (int j = 0; j < F::N; j++) {
+    x.v[j] = a[i * F::N + j];
+    y.v[j] = b[i * F::N + j];
+  }
+  if (op == 0) r = fe_mul(x, y);
+  else if (op == 1) r = fe_add(x, y);
+  else if (op == 2) r = fe_sub(x, y);
+  else r = fe_inv(x);
+  for (int j = 0; j < F::N; j++) out[i * F::N + j] = r.v[j];
+}
+
+extern "C" {
+
+const char* msm_b200_global_error(void) { return g_err.c_str(); }
+
+const char* msm_b200_last_error(const msm_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
+  msm_b200_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, MSM_E_INVALID, "null out pointer");
+  *out = nullptr;
+  if (curve < 0 || curve > 2) return fail(nullptr, MSM_E_INVALID, "unknown curve");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(nullptr, MSM_E_CUDA, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  ctx = new msm_b200_ctx();
+  ctx->device = device;
+  ctx->curve = curve;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return fail(nullptr, MSM_E_CUDA, cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+  }
+  cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, (MAX_ROUNDS + 2) * 8);
+  cudaError_t e2 = cudaMallocHost((void**)&ctx->h_result, 64 * 4);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, MSM_E_CUDA, "pinned allocation failed");
+  }
+  *out = ctx;
+  return 0;
+}
+
+void msm_b200_destroy(msm_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* all[] = {&ctx->bases, &ctx->raw_points, &ctx->raw_scalars, &ctx->hs, &ctx->cnt, &ctx->cursor, &ctx->po,
+                   &ctx->totals, &ctx->ent, &ctx->pairkey[0], &ctx->pairkey[1], &ctx->elem[0], &ctx->elem[1],
+                   &ctx->prefix, &ctx->red[0], &ctx->red[1], &ctx->partial, &ctx->result, &ctx->buckets, &ctx->rp_tables};
+  for (DevBuf* b : all) release(*b);
+  for (int i = 0; i < 8; i++) {
+    release(ctx->lvl_pre[i]);
+    release(ctx->lvl_tot[i]);
+  }
+  for (auto e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device) {
+  int rc = set_bases_impl(ctx, points, n, layout, on_device);
+  if (rc == 0 && ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return rc;
+}
+
+int msm_b200_run_partial(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_layout, int on_device, int form,
+                         int window_bits, void* partial_dev, msm_b200_timing* timing) {
+  if (!partial_dev) return fail(ctx, MSM_E_INVALID, "null partial pointer");
+  auto w0 = std::chrono::steady_clock::now();
+  if (ctx) ctx->launches = 0;
+  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, timing));
+  CK(cudaMemcpyAsync(partial_dev, ctx->partial.p, partial_bytes(ctx->curve), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (timing)
+    timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  return 0;
+}
+
+size_t msm_b200_partial_bytes(const msm_b200_ctx* ctx) { return ctx ? partial_bytes(ctx->curve) : 0; }
+
+int msm_b200_combine(msm_b200_ctx* ctx, const void* partials_dev, int count, msm_b200_point* out) {
+  return combine_impl(ctx, partials_dev, count, out);
+}
+
+int msm_b200_run(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_layout, int on_device, int form,
+                 int window_bits, msm_b200_point* out, msm_b200_timing* timing) {
+  if (!out) return fail(ctx, MSM_E_INVALID, "null out pointer");
+  auto w0 = std::chrono::steady_clock::now();
+  if (ctx) ctx->launches = 0;
+  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, timing));
+  Timer T(ctx);
+  int d0 = T.mark();
+  RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
+  int d1 = T.mark();
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (timing) {
+    timing->d2h_ms = T.ms(d0, d1);
+    timing->kernel_launches = ctx->launches;
+    timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  }
+  return 0;
+}
+
+int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, const void* points, int point_layout,
+                 size_t n, int form, int window_bits, msm_b200_point* out, msm_b200_timing* timing) {
+  if (!out) return fail(ctx, MSM_E_INVALID, "null out pointer");
+  auto w0 = std::chrono::steady_clock::now();
+  if (ctx) ctx->launches = 0;
+  Timer T(ctx ? ctx : nullptr);
+  int i0 = ctx ? T.mark() : 0;
+  RET_IF(set_bases_impl(ctx, points, n, point_layout, 0));
+  int i1 = T.mark();
+  int launches0 = ctx->launches;
+  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, timing));
+  RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
+  if (timing) {
+    timing->ingest_ms = T.ms(i0, i1);
+    timing->kernel_launches = ctx->launches + launches0;
+    timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  }
+  return 0;
+}
+
+size_t msm_b200_point_bytes(const msm_b200_ctx* ctx, int layout) { return ctx ? point_bytes(ctx->curve, layout) : 0; }
+size_t msm_b200_scalar_bytes(const msm_b200_ctx* ctx, int layout) {
+  (void)ctx;
+  return scalar_bytes(layout);
+}
+
+int msm_b200_dev_alloc(msm_b200_ctx* ctx, void** out_dev, size_t bytes) {
+  if (!ctx || !out_dev) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(out_dev, bytes ? bytes : 16));
+  return 0;
+}
+int msm_b200_dev_free(msm_b200_ctx* ctx, void* dev) {
+  if (!ctx) return fail(ctx, MSM_E_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(dev));
+  return 0;
+}
+int msm_b200_host_alloc_pinned(void** out_host, size_t bytes) {
+  msm_b200_ctx* ctx = nullptr;
+  if (!out_host) return fail(nullptr, MSM_E_INVALID, "null out pointer");
+  CK(cudaMallocHost(out_host, bytes ? bytes : 16));
+  return 0;
+}
+int msm_b200_host_free_pinned(void* host) {
+  msm_b200_ctx* ctx = nullptr;
+  CK(cudaFreeHost(host));
+  return 0;
+}
+int msm_b200_memcpy_d2h(msm_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return fail(ctx, MSM_E_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return fail(ctx, MSM_E_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int msm_b200_random_points(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  if (!ctx || !dst_dev) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  return ops_of(ctx->curve)->random_points(ctx, dst_dev, n, seed);
+}
+
+int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  if (!ctx || !dst_dev) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  return ops_of(ctx->curve)->random_scalars(ctx, dst_dev, n, seed);
+}
+
+// ---- test / measurement hooks ----
+int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host, const uint32_t* b_host,
+                           uint32_t* out_host, size_t n) {
+  msm_b200_ctx* ctx = nullptr;
+  if (field < 0 || field > 2 || op < 0 || op > 3 || !a_host || !b_host || !out_host)
+    return fail(nullptr, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(device));
+  int N = field == 0 ? 12 : 8;
+  size_t bytes = n * N * 4;
+  uint32_t *a, *b, *o;
+  CK(cudaMalloc(&a, bytes));
+  CK(cudaMalloc(&b, bytes));
+  CK(cudaMalloc(&o, bytes));
+  CK(cudaMemcpy(a, a_host, bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b, b_host, bytes, cudaMemcpyHostToDevice));
+  unsigned grid = cdiv(n, 64);
+  if (field == 0) k_test_field<Bls377Fq><<<grid, 64>>>(op, a, b, o, n);
+  else if (field == 1) k_test_field<PallasFp><<<grid, 64>>>(op, a, b, o, n);
+  else k_test_field<Bls377Fr><<<grid, 64>>>(op, a, b, o, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out_host, o, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(a);
+  cudaFree(b);
+  cudaFree(o);
+  return 0;
+}
+
+int msm_b200_test_digits(msm_b200_ctx* ctx, const void* scalars_host, size_t n, int window_bits, uint32_t* digits_host,
+                         int* n_windows) {
+  if (!ctx || !scalars_host || !digits_host || n == 0) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  if (ctx->curve == MSM_CURVE_ED_ON_BLS12_377) return fail(ctx, MSM_E_INVALID, "GLV digits need a Weierstrass curve");
+  CK(cudaSetDevice(ctx->device));
+  int c = window_bits > 0 ? window_bits : 13;
+  int b = ctx->curve == MSM_CURVE_BLS12_377_G1 ? 126 : 127;
+  int K = (b + 1 + c - 1) / c;
+  uint32_t* d_dig;
+  CK(cudaMalloc(&d_dig, 2 * n * K * 4));
+  size_t saved = ctx->n_bases;
+  ctx->n_bases = n;  // digits need no bases
+  msm_b200_timing tm;
+  int rc = run_partial_impl(ctx, scalars_host, n, MSM_LAYOUT_LE_BYTES, 0, MSM_FORM_AFFINE_GLV, c, &tm, d_dig);
+  ctx->n_bases = saved;
+  if (rc == 0) {
+    cudaMemcpy(digits_host, d_dig, 2 * n * K * 4, cudaMemcpyDeviceToHost);
+    if (n_windows) *n_windows = K;
+  }
+  cudaFree(d_dig);
+  return rc;
+}
+
+int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, float* ms_out) {
+  msm_b200_ctx* ctx = nullptr;
+  if (!ops_per_sec || iters < 1) return fail(nullptr, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  uint32_t* d;
+  CK(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int blocks = prop.multiProcessorCount * 4, threads = 256;
+  double ops = 0;
+  for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    CK(cudaEventRecord(e0));
+    switch (which) {
+      case 0: k_mb_imad<0><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 1: k_mb_imad<1><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 2: k_mb_imad<2><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 5: k_mb_imad<5><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 3: k_mb_modmul<Bls377Fq><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 4: k_mb_modmul<PallasFp><<<blocks, threads>>>(d, iters, 12345u); break;
+      default: cudaFree(d); return fail(nullptr, MSM_E_INVALID, "unknown benchmark");
+    }
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+  }
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (which == 3 || which == 4)
+    ops = (double)blocks * threads * iters * 2.0;
+  else
+    ops = (double)blocks * threads * iters * (double)MB_INNER * MB_CHAINS;
+  *ops_per_sec = ops / (ms * 1e-3);
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,528 @@
+// Host orchestration templates of libmsm_b200.so (instantiated once per curve in curve_*.cu).
+// One context = one GPU + one curve.  All device work goes to ctx->stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/msm_b200.h"
+#include "kernels_weierstrass.cuh"
+#include "kernels_basic.cuh"
+
+using namespace msm;
+
+std::string& msm_global_err();
+#define g_err (msm_global_err())
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct msm_b200_ctx {
+  int device = 0;
+  int curve = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int launches = 0;
+  // resident bases
+  DevBuf bases;
+  size_t n_bases = 0;
+  // workspace
+  DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
+  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables;
+  unsigned long long* h_totals = nullptr;  // pinned
+  uint32_t* h_result = nullptr;            // pinned
+  std::vector<cudaEvent_t> ev;
+};
+
+#define CK(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char buf_[512];                                                                        \
+      snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      if (ctx) ctx->err = buf_;                                                              \
+      g_err = buf_;                                                                          \
+      return (e_ == cudaErrorMemoryAllocation) ? MSM_E_NOMEM : MSM_E_CUDA;                   \
+    }                                                                                        \
+  } while (0)
+
+#define RET_IF(x)           \
+  do {                      \
+    int rc_ = (x);          \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+static int fail(msm_b200_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+static int ensure(msm_b200_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return 0;
+  if (b.p) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 16;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    CK(cudaMalloc(&b.p, want));
+  }
+  b.cap = want;
+  return 0;
+}
+
+static void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+#define LAUNCH(ctx, kern, grid, block, ...)                          \
+  do {                                                               \
+    kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);        \
+    (ctx)->launches++;                                               \
+  } while (0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static int ceil_log2_sz(size_t n) {
+  int k = 0;
+  while (((size_t)1 << k) < n) k++;
+  return k;
+}
+
+struct Timer {
+  msm_b200_ctx* ctx;
+  std::vector<cudaEvent_t>& ev;
+  size_t used = 0;
+  explicit Timer(msm_b200_ctx* c) : ctx(c), ev(c->ev) {}
+  int mark() {  // records an event, returns its index
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    cudaEventRecord(ev[used], ctx->stream);
+    return (int)used++;
+  }
+  float ms(int a, int b) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ev[a], ev[b]);
+    return t;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// curve dispatch helpers
+// ------------------------------------------------------------------------------------------
+static int field_limbs(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 12 : 8; }
+static int field_limbs29(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 14 : 9; }
+static int field_bytes(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 48 : 32; }
+
+static size_t point_bytes(int curve, int layout) {
+  if (layout == MSM_LAYOUT_LE_BYTES) return 2 * (size_t)field_bytes(curve);
+  if (curve == MSM_CURVE_ED_ON_BLS12_377) return 4 * 4 * (size_t)field_limbs29(curve);
+  return 2 * 4 * (size_t)field_limbs29(curve) + 4;
+}
+static size_t scalar_bytes(int layout) { return layout == MSM_LAYOUT_LE_BYTES ? 32 : 36; }
+
+// engine default window size (the reference's table is tuned for 16 CPU threads,
+// src/msm-common.ts:33-57; any c gives the same result)
+static int default_window(int curve, int form, size_t n) {
+  int lg = ceil_log2_sz(n);
+  int c;
+  if (form == MSM_FORM_AFFINE_GLV) {
+    c = lg - 5;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+  } else {
+    c = lg - 6;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+  }
+  (void)curve;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// set_bases
+// ------------------------------------------------------------------------------------------
+template <class F>
+static int ingest_weierstrass(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout) {
+  RET_IF(ensure(ctx, ctx->bases, n * 2 * (2 * F::N * 4)));
+  LAUNCH(ctx, k_ingest_points<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class F>
+static int ingest_te(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout) {
+  RET_IF(ensure(ctx, ctx->bases, n * (3 * F::N * 4)));
+  LAUNCH(ctx, k_te_ingest<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched inversion of the thread totals of one round (upper levels of the product tree)
+// level 0 totals live in lvl_tot[0] (M1 elements); on return lvl_pre[0] holds their inverses.
+// ------------------------------------------------------------------------------------------
+template <class F>
+static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
+  constexpr size_t FE = F::N * 4;
+  size_t M[8];
+  int nl = 0;
+  M[0] = M1;
+  // lvl_tot[l] = values of level l+1 (M[l] elements); lvl_pre[l] = their prefixes, then inverses
+  while (M[nl] > (size_t)TOP_MAX && nl < 6) {
+    size_t blocks = cdiv(M[nl], (size_t)UP_THREADS * UP_B1);
+    M[nl + 1] = blocks * UP_THREADS;
+    nl++;
+  }
+  for (int l = 0; l <= nl; l++) RET_IF(ensure(ctx, ctx->lvl_pre[l], M[l] * FE));
+  for (int l = 1; l <= nl; l++) RET_IF(ensure(ctx, ctx->lvl_tot[l], M[l] * FE));
+  for (int l = 0; l < nl; l++) {
+    LAUNCH(ctx, k_up_fwd<F>, cdiv(M[l], (size_t)UP_THREADS * UP_B1), UP_THREADS, (const uint4*)ctx->lvl_tot[l].p, M[l],
+           (uint4*)ctx->lvl_pre[l].p, (uint4*)ctx->lvl_tot[l + 1].p, M[l + 1]);
+  }
+  LAUNCH(ctx, k_inv_top<F>, cdiv(M[nl], 32), 32, (const uint4*)ctx->lvl_tot[nl].p, M[nl], (uint4*)ctx->lvl_pre[nl].p);
+  for (int l = nl - 1; l >= 0; l--) {
+    LAUNCH(ctx, k_up_bwd<F>, cdiv(M[l], (size_t)UP_THREADS * UP_B1), UP_THREADS, (const uint4*)ctx->lvl_tot[l].p, M[l],
+           (uint4*)ctx->lvl_pre[l].p, (const uint4*)ctx->lvl_pre[l + 1].p, M[l + 1]);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket reduction + Horner -> partial result in ctx->partial (any curve form)
+// ------------------------------------------------------------------------------------------
+template <class C, class Loader>
+static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K, int c) {
+  constexpr size_t ITEM = (size_t)item_u4<C>() * 16;
+  int remaining = c - 1;
+  int gb = remaining < 3 ? remaining : 3;
+  size_t items = NB >> gb;
+  RET_IF(ensure(ctx, ctx->red[0], items * ITEM));
+  RET_IF(ensure(ctx, ctx->red[1], (items / 2 + 1) * ITEM));
+  LAUNCH(ctx, (k_reduce0<C, Loader>), cdiv(items, 64), 64, ld, (uint32_t)NB, gb, (uint4*)ctx->red[0].p);
+  remaining -= gb;
+  int cur = 0;
+  while (remaining > 0) {
+    gb = remaining < 3 ? remaining : 3;
+    size_t out_items = items >> gb;
+    LAUNCH(ctx, (k_reduce_up<C>), cdiv(out_items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
+           (uint4*)ctx->red[cur ^ 1].p);
+    items = out_items;
+    remaining -= gb;
+    cur ^= 1;
+  }
+  RET_IF(ensure(ctx, ctx->partial, 4 * 12 * 4));
+  LAUNCH(ctx, (k_horner<C>), 1, 32, (const uint4*)ctx->red[cur].p, K, c, (uint4*)ctx->partial.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic bucket method (msmBasic): twisted Edwards and msmProjective
+// ------------------------------------------------------------------------------------------
+template <class C, class S>
+static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, int layout, int c,
+                            msm_b200_timing* tm) {
+  using F = typename C::F;
+  constexpr size_t FE = F::N * 4;
+  Timer T(ctx);
+  const int b = S::QBITS;  // Scalar.sizeInBits, src/msm-basic.ts:55
+  const int K = (b + 1 + c - 1) / c;
+  const uint32_t L = 1u << (c - 1);
+  const size_t NB = (size_t)K * L;
+  if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
+  int e0 = T.mark();
+  RET_IF(ensure(ctx, ctx->hs, n * 32));
+  RET_IF(ensure(ctx, ctx->cnt, NB * 4));
+  RET_IF(ensure(ctx, ctx->cursor, NB * 4));
+  RET_IF(ensure(ctx, ctx->po, NB * 4));
+  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 2) * 8));
+  LAUNCH(ctx, k_load_scalars<S>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
+  CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
+  SortArgs sa;
+  sa.hs = (const uint4*)ctx->hs.p;
+  sa.S = n;
+  sa.c = c;
+  sa.K = K;
+  sa.L = L;
+  sa.cnt = (uint32_t*)ctx->cnt.p;
+  sa.cursor = (uint32_t*)ctx->cursor.p;
+  sa.po0 = (const uint32_t*)ctx->po.p;
+  sa.ent = nullptr;
+  sa.pairkey = nullptr;
+  sa.digits = nullptr;
+  LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
+  int e1 = T.mark();
+  LAUNCH(ctx, k_scan, 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
+         (unsigned long long*)ctx->totals.p);
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t P0 = ctx->h_totals[0];
+  RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
+  sa.ent = (uint32_t*)ctx->ent.p;
+  LAUNCH(ctx, k_hist_scatter8<true>, cdiv(n, 256), 256, sa);
+  int e2 = T.mark();
+  RET_IF(ensure(ctx, ctx->buckets, NB * C::ACC_FE * FE));
+  int h0 = T.mark();
+  LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
+         (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);
+  int h1 = T.mark();
+  CK(cudaGetLastError());
+  int e3 = T.mark();
+  AccBucketLoader<C> ld;
+  ld.buckets = (const uint4*)ctx->buckets.p;
+  RET_IF((reduce_buckets<C>(ctx, ld, NB, K, c)));
+  int e4 = T.mark();
+  if (tm) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    tm->digits_ms = T.ms(e0, e1);
+    tm->sort_ms = T.ms(e1, e2);
+    tm->accumulate_ms = T.ms(e2, e3);
+    tm->reduce_ms = T.ms(e3, e4);
+    tm->hot_kernel_ms = T.ms(h0, h1);
+    tm->hot_kernel_launches = 1;
+    tm->window_bits = c;
+    tm->n_windows = K;
+    tm->rounds = 0;
+    tm->n_adds = 0;  // filled by the caller from the histogram if needed
+  }
+  return 0;
+}
+
+template <class C>
+static int finalize_any(msm_b200_ctx* ctx, const void* partials_dev, int count, msm_b200_point* out) {
+  using F = typename C::F;
+  RET_IF(ensure(ctx, ctx->result, (2 * F::N + 1) * 4));
+  LAUNCH(ctx, (k_finalize<C>), 1, 32, (const uint4*)partials_dev, count, (uint32_t*)ctx->result.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_result, ctx->result.p, (2 * F::N + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memset(out, 0, sizeof *out);
+  memcpy(out->x, ctx->h_result, F::N * 4);
+  memcpy(out->y, ctx->h_result + F::N, F::N * 4);
+  out->is_zero = (int32_t)ctx->h_result[2 * F::N];
+  return 0;
+}
+
+template <class C, class S>
+static int random_points_t(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  using F = typename C::F;
+  size_t entries = (size_t)RP_TABLES << RP_BITS;
+  RET_IF(ensure(ctx, ctx->rp_tables, entries * 2 * F::N * 4));
+  LAUNCH(ctx, k_rp_tables<C>, cdiv(entries, 64), 64, (uint4*)ctx->rp_tables.p, seed);
+  size_t threads = (n + RP_BATCH - 1) / RP_BATCH;
+  LAUNCH(ctx, k_rp_points<C>, cdiv(threads, 64), 64, (const uint4*)ctx->rp_tables.p, (uint8_t*)dst_dev, n,
+         seed ^ 0x5EEDull);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weierstrass GLV batched-affine MSM -> projective partial in ctx->partial
+// ------------------------------------------------------------------------------------------
+template <class F, class G, uint32_t B3>
+static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, int layout, int c,
+                          msm_b200_timing* tm, uint32_t* digits_dump_dev) {
+  constexpr size_t FE = F::N * 4;
+  Timer T(ctx);
+  const int b = G::QBITS == 253 ? 126 : 127;  // Scalar.maxBits, src/wasm/glv.ts:216-226
+  const int K = (b + 1 + c - 1) / c;
+  const uint32_t L = 1u << (c - 1);
+  const size_t NB = (size_t)K * L;
+  const size_t S = 2 * n;
+  if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
+
+  int e0 = T.mark();
+  // --- GLV + digits + histogram
+  RET_IF(ensure(ctx, ctx->hs, S * 16));
+  RET_IF(ensure(ctx, ctx->cnt, NB * 4));
+  RET_IF(ensure(ctx, ctx->cursor, NB * 4));
+  RET_IF(ensure(ctx, ctx->po, (size_t)(MAX_ROUNDS + 1) * NB * 4));
+  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 2) * 8));
+  LAUNCH(ctx, k_glv<G>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
+  CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
+  SortArgs sa;
+  sa.hs = (const uint4*)ctx->hs.p;
+  sa.S = S;
+  sa.c = c;
+  sa.K = K;
+  sa.L = L;
+  sa.cnt = (uint32_t*)ctx->cnt.p;
+  sa.cursor = (uint32_t*)ctx->cursor.p;
+  sa.po0 = (const uint32_t*)ctx->po.p;
+  sa.ent = nullptr;
+  sa.pairkey = nullptr;
+  sa.digits = digits_dump_dev;
+  LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
+  int e1 = T.mark();
+  // --- offsets for every round, one host sync
+  LAUNCH(ctx, k_scan, MAX_ROUNDS + 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
+         (unsigned long long*)ctx->totals.p);
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const unsigned long long maxcnt = ctx->h_totals[MAX_ROUNDS + 1];
+  int R = 1;
+  while (((unsigned long long)1 << R) < maxcnt) R++;
+  if (R > MAX_ROUNDS - 1) return fail(ctx, MSM_E_INVALID, "bucket too large");
+  const size_t P0 = ctx->h_totals[0];
+  if (digits_dump_dev) {  // tests only need the digits
+    if (tm) {
+      tm->window_bits = c;
+      tm->n_windows = K;
+    }
+    return 0;
+  }
+  unsigned long long n_adds = 0;
+  // --- scatter
+  RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
+  RET_IF(ensure(ctx, ctx->pairkey[0], (P0 + 1) * 4));
+  RET_IF(ensure(ctx, ctx->pairkey[1], (ctx->h_totals[1] + 1) * 4));
+  sa.ent = (uint32_t*)ctx->ent.p;
+  sa.pairkey = (uint32_t*)ctx->pairkey[0].p;
+  LAUNCH(ctx, k_hist_scatter<true>, cdiv(S, 256), 256, sa);
+  int e2 = T.mark();
+  // --- tree rounds
+  RET_IF(ensure(ctx, ctx->elem[0], ElemBuf<F>::bytes(ctx->h_totals[1] + 1)));
+  RET_IF(ensure(ctx, ctx->elem[1], ElemBuf<F>::bytes(ctx->h_totals[2] + 1)));
+  RET_IF(ensure(ctx, ctx->prefix, (P0 + 1) * FE));
+  std::vector<std::pair<int, int>> hot;
+  for (int r = 0; r < R; r++) {
+    const size_t P = ctx->h_totals[r];
+    const size_t Pn = ctx->h_totals[r + 1];
+    RoundArgs<F> a;
+    a.r = r;
+    a.P = P;
+    a.cnt = (const uint32_t*)ctx->cnt.p;
+    a.po_r = (const uint32_t*)ctx->po.p + (size_t)r * NB;
+    a.po_n = (const uint32_t*)ctx->po.p + (size_t)(r + 1) * NB;
+    a.pairkey = (const uint32_t*)ctx->pairkey[r & 1].p;
+    a.pairkey_next = (uint32_t*)ctx->pairkey[(r + 1) & 1].p;
+    a.ent = (const uint32_t*)ctx->ent.p;
+    a.bases = (const uint4*)ctx->bases.p;
+    // elements of round r (r >= 1) live in elem[(r-1)&1] with capacity P_r; outputs go to elem[r&1]
+    a.in.base = (uint4*)ctx->elem[(r + 1) & 1].p;
+    a.in.cap = P;
+    a.out.base = (uint4*)ctx->elem[r & 1].p;
+    a.out.cap = Pn;
+    unsigned grid = cdiv(P, (size_t)ACC_THREADS * ACC_B0);
+    size_t M1 = (size_t)grid * ACC_THREADS;
+    RET_IF(ensure(ctx, ctx->lvl_tot[0], M1 * FE));
+    RET_IF(ensure(ctx, ctx->lvl_pre[0], M1 * FE));
+    a.prefix = (uint4*)ctx->prefix.p;
+    a.tot = (uint4*)ctx->lvl_tot[0].p;
+    a.invtot = (const uint4*)ctx->lvl_pre[0].p;
+    a.M1 = M1;
+    if (r == 0)
+      LAUNCH(ctx, (k_fwd<F, true>), grid, ACC_THREADS, a);
+    else
+      LAUNCH(ctx, (k_fwd<F, false>), grid, ACC_THREADS, a);
+    RET_IF(invert_totals<F>(ctx, M1));
+    int h0 = T.mark();
+    if (r == 0)
+      LAUNCH(ctx, (k_bwd<F, true>), grid, ACC_THREADS, a);
+    else
+      LAUNCH(ctx, (k_bwd<F, false>), grid, ACC_THREADS, a);
+    int h1 = T.mark();
+    hot.push_back({h0, h1});
+    n_adds += P;  // upper bound: includes pass-through singles
+  }
+  CK(cudaGetLastError());
+  int e3 = T.mark();
+  // --- bucket reduction
+  {
+    AffineBucketLoader<F, B3> ld;
+    ld.last.base = (uint4*)ctx->elem[(R - 1) & 1].p;
+    ld.last.cap = ctx->h_totals[R];
+    ld.cnt = (const uint32_t*)ctx->cnt.p;
+    ld.po_last = (const uint32_t*)ctx->po.p + (size_t)R * NB;
+    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
+  }
+  int e4 = T.mark();
+  if (tm) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    tm->digits_ms = T.ms(e0, e1);
+    tm->sort_ms = T.ms(e1, e2);
+    tm->accumulate_ms = T.ms(e2, e3);
+    tm->reduce_ms = T.ms(e3, e4);
+    tm->hot_kernel_ms = 0;
+    for (auto& h : hot) tm->hot_kernel_ms += T.ms(h.first, h.second);
+    tm->hot_kernel_launches = (int)hot.size();
+    tm->window_bits = c;
+    tm->n_windows = K;
+    tm->rounds = R;
+    tm->n_adds = n_adds;
+  }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// per-curve entry points (one translation unit each, so the curves build in parallel)
+// ------------------------------------------------------------------------------------------
+struct CurveOps {
+  int (*ingest)(msm_b200_ctx*, const void* d_in, size_t n, int layout);
+  int (*run)(msm_b200_ctx*, const void* d_scalars, size_t n, int layout, int form, int c, msm_b200_timing*,
+             uint32_t* digits_dump_dev);
+  int (*zero_partial)(msm_b200_ctx*);
+  int (*finalize)(msm_b200_ctx*, const void* partials_dev, int count, msm_b200_point* out);
+  int (*random_points)(msm_b200_ctx*, void* dst_dev, size_t n, uint64_t seed);
+  int (*random_scalars)(msm_b200_ctx*, void* dst_dev, size_t n, uint64_t seed);
+};
+const CurveOps* curve_ops_bls377();
+const CurveOps* curve_ops_pallas();
+const CurveOps* curve_ops_ed377();
+
+template <class C>
+static int zero_partial_t(msm_b200_ctx* ctx) {
+  RET_IF(ensure(ctx, ctx->partial, 4 * 12 * 4));
+  LAUNCH(ctx, (k_zero_partial<C>), 1, 32, (uint4*)ctx->partial.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <class S>
+static int random_scalars_t(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  LAUNCH(ctx, k_random_scalars<S>, cdiv(n, 256), 256, (uint32_t*)dst_dev, n, seed);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Weierstrass curve with GLV: forms AFFINE_GLV and PROJECTIVE
+template <class F, class G, uint32_t B3>
+static int run_weierstrass_t(msm_b200_ctx* ctx, const void* d_s, size_t n, int layout, int form, int c,
+                             msm_b200_timing* tm, uint32_t* digits_dump_dev) {
+  if (form == MSM_FORM_AFFINE_GLV) return run_affine_glv<F, G, B3>(ctx, d_s, n, layout, c, tm, digits_dump_dev);
+  return run_bucket_basic<WeierCurve<F, B3>, G>(ctx, d_s, n, layout, c, tm);
+}
+
+#define MSM_DEFINE_WEIERSTRASS_CURVE(fn, F, G, B3)                                                          \
+  const CurveOps* fn() {                                                                                    \
+    static const CurveOps ops = {ingest_weierstrass<F>,          run_weierstrass_t<F, G, B3>,                \
+                                 zero_partial_t<WeierCurve<F, B3>>, finalize_any<WeierCurve<F, B3>>,         \
+                                 random_points_t<WeierCurve<F, B3>, G>, random_scalars_t<G>};                \
+    return &ops;                                                                                            \
+  }

@@ -1,0 +1,379 @@
+// Prime-field arithmetic on 32-bit limbs held in registers (Montgomery form, R = 2^(32 N)).
+//
+// Replaces the reference's runtime-generated wasm field module:
+//   multiply / square            src/wasm/multiply-montgomery.ts:58-215  (29-bit limbs, i64 locals)
+//   add / subtract / reduce      src/wasm/field-arithmetic.ts:32-166
+//   inverse                      src/wasm/inverse.ts:42-218
+// The representation differs on purpose (only the normalised affine output is
+// compared): values are kept CANONICAL in [0, p) so that equality tests are limb compares.
+//
+// Multiplication is operand scanning with the products of even and odd limbs of `a` kept in two
+// separate accumulators (one word apart), so that every 32x32->64 product lands on an aligned
+// register pair and each row is two independent `mad.lo.cc / madc.hi.cc` carry chains -- ptxas
+// fuses each lo/hi pair into one IMAD.WIDE.U32(.X) with the carry in a predicate register.
+//
+// The same source compiles for the host (carry flag emulated) so that the math core can be unit
+// tested without a GPU (tests/test_hostmath.py); kernels never run on the host.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MSM_HD __host__ __device__ __forceinline__
+#else
+#define MSM_HD inline
+#endif
+
+namespace msm {
+
+// ------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+#else
+// Host emulation of the PTX condition-code carry flag (unit tests only).
+inline uint32_t& msm_cf() {
+  static thread_local uint32_t cf = 0;
+  return cf;
+}
+inline uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b;
+  msm_cf() = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+inline uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b + msm_cf();
+  msm_cf() = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+inline uint32_t addc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a + b + msm_cf()); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b;
+  msm_cf() = (uint32_t)((t >> 32) & 1);  // borrow
+  return (uint32_t)t;
+}
+inline uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b - msm_cf();
+  msm_cf() = (uint32_t)((t >> 32) & 1);
+  return (uint32_t)t;
+}
+inline uint32_t subc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a - b - msm_cf()); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// field element
+// ------------------------------------------------------------------------------------------
+template <class F>
+struct Fe {
+  uint32_t v[F::N];
+};
+
+template <class F>
+MSM_HD bool fe_is_zero(const Fe<F>& a) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) acc |= a.v[i];
+  return acc == 0;
+}
+
+template <class F>
+MSM_HD bool fe_eq(const Fe<F>& a, const Fe<F>& b) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) acc |= a.v[i] ^ b.v[i];
+  return acc == 0;
+}
+
+template <class F>
+MSM_HD Fe<F> fe_zero() {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = 0;
+  return r;
+}
+
+template <class F>
+MSM_HD Fe<F> fe_one() {  // Montgomery form of 1
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = F::ONE(i);
+  return r;
+}
+
+// r = a - p if a >= p else a      (a < 2p)
+template <class F>
+MSM_HD void fe_reduce_once(Fe<F>& a) {
+  uint32_t t[F::N];
+  t[0] = sub_cc(a.v[0], F::P(0));
+#pragma unroll
+  for (int i = 1; i < F::N; i++) t[i] = subc_cc(a.v[i], F::P(i));
+  uint32_t borrow = subc(0u, 0u);  // 0xffffffff if a < p
+#pragma unroll
+  for (int i = 0; i < F::N; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+// (a + b) mod p, canonical inputs    (src/wasm/field-arithmetic.ts:32-63 `add`)
+template <class F>
+MSM_HD Fe<F> fe_add(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < F::N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  r.v[F::N - 1] = addc(a.v[F::N - 1], b.v[F::N - 1]);  // 2p < 2^(32N): no carry out
+  fe_reduce_once(r);
+  return r;
+}
+
+// (a - b) mod p, canonical inputs    (src/wasm/field-arithmetic.ts:65-100 `subtract`)
+template <class F>
+MSM_HD Fe<F> fe_sub(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> r;
+  r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < F::N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = subc(0u, 0u);  // all ones if a < b
+  r.v[0] = add_cc(r.v[0], F::P(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < F::N - 1; i++) r.v[i] = addc_cc(r.v[i], F::P(i) & borrow);
+  r.v[F::N - 1] = addc(r.v[F::N - 1], F::P(F::N - 1) & borrow);
+  return r;
+}
+
+template <class F>
+MSM_HD Fe<F> fe_neg(const Fe<F>& a) {
+  return fe_sub(fe_zero<F>(), a);
+}
+
+template <class F>
+MSM_HD Fe<F> fe_dbl(const Fe<F>& a) {
+  return fe_add(a, a);
+}
+
+template <class F>
+MSM_HD Fe<F> fe_select(bool c, const Fe<F>& a, const Fe<F>& b) {  // c ? a : b
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Montgomery product  a*b*2^(-32N) mod p, canonical in/out.
+// (replaces src/wasm/multiply-montgomery.ts:58-136)
+//
+// State between rows: two accumulators.  X is word aligned (word w has weight 2^(32w), N+1
+// words), Y sits one word higher (word w has weight 2^(32(w+1)), N words); T = X + Y*2^32.
+// Row i adds a*b_i (even limbs of a into X, odd limbs into Y), then m*p with m = -T_0/p mod 2^32
+// the same way, which clears X_0.  Dividing by 2^32 swaps the roles: new X = Y, new Y_w = X_(w+2)
+// and the stray word X_1 is added into new X_0 with its carry entering the new Y chain.
+// Bounds (a, b < p): T < 2p < 2^(32N) at every row end, so Y never carries out of word N-1.
+// ------------------------------------------------------------------------------------------
+template <class F, bool FIRST>
+MSM_HD void mont_row(uint32_t* U, uint32_t* V, const uint32_t* a, uint32_t bi) {
+  constexpr int N = F::N;
+  // On entry (not FIRST): U = previous X (N+1 words), V = previous Y (N words, V[N] unused).
+  // On exit: V = X (N+1 words), U = Y (N words)  -- before the division by 2^32.
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      V[j] = mul_lo(a[j], bi);
+      V[j + 1] = mul_hi(a[j], bi);
+      U[j] = mul_lo(a[j + 1], bi);
+      U[j + 1] = mul_hi(a[j + 1], bi);
+    }
+    V[N] = 0;
+  } else {
+    // stray word, then the odd-limb chain reading U two words up
+    V[0] = add_cc(V[0], U[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      U[j] = madc_lo_cc(a[j + 1], bi, U[j + 2]);
+      U[j + 1] = madc_hi_cc(a[j + 1], bi, (j + 3 <= N) ? U[j + 3] : 0u);
+    }
+    U[N - 2] = madc_lo_cc(a[N - 1], bi, U[N]);
+    U[N - 1] = madc_hi(a[N - 1], bi, 0u);
+    // even-limb chain
+    V[0] = mad_lo_cc(a[0], bi, V[0]);
+    V[1] = madc_hi_cc(a[0], bi, V[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      V[j] = madc_lo_cc(a[j], bi, V[j]);
+      V[j + 1] = madc_hi_cc(a[j], bi, V[j + 1]);
+    }
+    V[N] = addc(0u, 0u);
+  }
+  uint32_t m = mul_lo(V[0], F::M0);
+  // m*p, odd limbs of p into Y
+  U[0] = mad_lo_cc(F::P(1), m, U[0]);
+  U[1] = madc_hi_cc(F::P(1), m, U[1]);
+#pragma unroll
+  for (int j = 2; j < N - 2; j += 2) {
+    U[j] = madc_lo_cc(F::P(j + 1), m, U[j]);
+    U[j + 1] = madc_hi_cc(F::P(j + 1), m, U[j + 1]);
+  }
+  if (N > 2) {
+    U[N - 2] = madc_lo_cc(F::P(N - 1), m, U[N - 2]);
+    U[N - 1] = madc_hi(F::P(N - 1), m, U[N - 1]);
+  }
+  // even limbs of p into X
+  V[0] = mad_lo_cc(F::P(0), m, V[0]);
+  V[1] = madc_hi_cc(F::P(0), m, V[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    V[j] = madc_lo_cc(F::P(j), m, V[j]);
+    V[j + 1] = madc_hi_cc(F::P(j), m, V[j + 1]);
+  }
+  V[N] = addc(V[N], 0u);
+}
+
+template <class F>
+MSM_HD Fe<F> fe_mul(const Fe<F>& a, const Fe<F>& b) {
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0, "even limb count");
+  uint32_t A0[N + 1], A1[N + 1];
+  A0[N] = 0;
+  A1[N] = 0;
+  mont_row<F, true>(A0, A1, a.v, b.v[0]);  // X = A1, Y = A0
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_row<F, false>(A1, A0, a.v, b.v[i]);  // prev X = A1, prev Y = A0 -> X = A0, Y = A1
+    if (i + 1 < N) mont_row<F, false>(A0, A1, a.v, b.v[i + 1]);
+  }
+  // N even: the last row left X = A0 (N+1 words), Y = A1.   T = Y + (X >> 32)
+  Fe<F> r;
+  r.v[0] = add_cc(A1[0], A0[1]);
+#pragma unroll
+  for (int w = 1; w < N - 1; w++) r.v[w] = addc_cc(A1[w], A0[w + 1]);
+  r.v[N - 1] = addc(A1[N - 1], A0[N]);
+  fe_reduce_once(r);
+  return r;
+}
+
+template <class F>
+MSM_HD Fe<F> fe_sqr(const Fe<F>& a) {
+  return fe_mul(a, a);
+}
+
+// a * (small unsigned constant), by double-and-add on the constant's bits (c >= 1)
+template <class F>
+MSM_HD Fe<F> fe_mul_small(const Fe<F>& a, uint32_t c) {
+  Fe<F> r = a;
+  int top = 31;
+  while (!((c >> top) & 1)) top--;
+  for (int i = top - 1; i >= 0; i--) {
+    r = fe_dbl(r);
+    if ((c >> i) & 1) r = fe_add(r, a);
+  }
+  return r;
+}
+
+// Montgomery-domain inverse by Fermat: a^(p-2)   (a = x*R  ->  x^-1 * R).  a != 0.
+// Fixed 4-bit windows over the exponent p-2 (replaces src/wasm/inverse.ts:191-218).
+template <class F>
+MSM_HD Fe<F> fe_inv(const Fe<F>& a) {
+  Fe<F> tbl[16];
+  tbl[0] = fe_one<F>();
+  tbl[1] = a;
+#pragma unroll 1
+  for (int i = 2; i < 16; i++) tbl[i] = fe_mul(tbl[i - 1], a);
+  Fe<F> r = fe_one<F>();
+  bool started = false;
+#pragma unroll 1
+  for (int i = F::N * 8 - 1; i >= 0; i--) {
+    uint32_t nib = (F::PM2(i >> 3) >> ((i & 7) * 4)) & 15u;
+    if (started) {
+      r = fe_sqr(r);
+      r = fe_sqr(r);
+      r = fe_sqr(r);
+      r = fe_sqr(r);
+    }
+    if (nib) {
+      r = started ? fe_mul(r, tbl[nib]) : tbl[nib];
+      started = true;
+    }
+  }
+  return r;
+}
+
+// x -> x*R (to Montgomery) and back
+template <class F>
+MSM_HD Fe<F> fe_to_mont(const Fe<F>& a) {
+  Fe<F> r2;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r2.v[i] = F::R2(i);
+  return fe_mul(a, r2);
+}
+
+template <class F>
+MSM_HD Fe<F> fe_from_mont(const Fe<F>& a) {
+  Fe<F> one = fe_zero<F>();
+  one.v[0] = 1;
+  return fe_mul(a, one);
+}
+
+}  // namespace msm

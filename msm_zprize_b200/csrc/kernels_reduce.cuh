@@ -1,0 +1,205 @@
+// Bucket reduction, window combination and output normalisation, generic over the curve form.
+//
+// sum_l l * B_l per window is computed as a hierarchy of weighted sums.  Items (R_t, X_t) stand
+// for sum_t (t * R_t + X_t); one level groups g = 2^gb consecutive items:
+//     R'_u = g * sum_t R_t,      X'_u = sum_t ((t - u g) R_t + X_t)
+// (level 0: the items are the bucket sums with weights t+1 and X = 0).  This is the reference's
+// per-chunk running sum with the `triangle + (lstart-1) * row` identity
+// (src/msm-batched-affine.ts:530-571, src/msm-basic.ts:192-223) applied recursively, so every
+// level is data parallel instead of one chunk per CPU thread.  The last level leaves one item per
+// window whose X is the window sum; k_horner combines the windows (:310-321).
+#pragma once
+#include "kernels_common.cuh"
+
+namespace msm {
+
+// ---- curve-form traits ------------------------------------------------------------------
+template <class F_, uint32_t B3_>
+struct WeierCurve {
+  using F = F_;
+  using Acc = Proj<F>;
+  static constexpr int ACC_FE = 3;   // field elements per accumulator
+  static constexpr int BASE_FE = 2;  // field elements per cached base point (x | y)
+  static constexpr int BASE_STRIDE = 2;  // records per input point in ctx->bases (G, endo G)
+  __device__ static Acc zero() { return proj_zero<F>(); }
+  __device__ static Acc add(const Acc& a, const Acc& b) { return proj_add<F, B3_>(a, b); }
+  __device__ static Acc dbl(const Acc& a) { return proj_dbl<F, B3_>(a); }
+  __device__ static void st(uint4* p, const Acc& P) {
+    st_aos<F>(p, P.X);
+    st_aos<F>(p + F::N / 4, P.Y);
+    st_aos<F>(p + 2 * F::N / 4, P.Z);
+  }
+  __device__ static Acc ld(const uint4* p) {
+    Acc P;
+    P.X = ld_aos<F>(p);
+    P.Y = ld_aos<F>(p + F::N / 4);
+    P.Z = ld_aos<F>(p + 2 * F::N / 4);
+    return P;
+  }
+  // acc +/- base point `idx` (src/curve-projective.ts addMixed / subMixed)
+  __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
+    const uint4* p = bases + (size_t)idx * BASE_STRIDE * (2 * F::N / 4);
+    Aff<F> Q;
+    Q.x = ld_aos<F>(p);
+    Q.y = ld_aos<F>(p + F::N / 4);
+    if (aff_is_inf(Q)) return a;
+    if (neg) Q.y = fe_neg(Q.y);
+    return proj_add_mixed<F, B3_>(a, Q);
+  }
+  // canonical affine output words: x | y | is_zero
+  __device__ static void normalise(const Acc& a, uint32_t* out) {
+    Aff<F> A = proj_to_aff(a);
+    bool inf = aff_is_inf(A);
+    Fe<F> x = inf ? fe_zero<F>() : fe_from_mont(A.x);
+    Fe<F> y = inf ? fe_zero<F>() : fe_from_mont(A.y);
+    for (int i = 0; i < F::N; i++) {
+      out[i] = x.v[i];
+      out[F::N + i] = y.v[i];
+    }
+    out[2 * F::N] = inf ? 1u : 0u;
+  }
+};
+
+template <class F_>
+struct TeCurve {
+  using F = F_;
+  using Acc = Ext<F>;
+  static constexpr int ACC_FE = 4;
+  static constexpr int BASE_FE = 3;  // (y+x | y-x | 2d*x*y)
+  static constexpr int BASE_STRIDE = 1;
+  __device__ static Acc zero() { return ext_zero<F>(); }
+  __device__ static Acc add(const Acc& a, const Acc& b) { return ext_add<F>(a, b); }
+  __device__ static Acc dbl(const Acc& a) { return ext_dbl<F>(a); }
+  __device__ static void st(uint4* p, const Acc& P) {
+    st_aos<F>(p, P.X);
+    st_aos<F>(p + F::N / 4, P.Y);
+    st_aos<F>(p + 2 * F::N / 4, P.Z);
+    st_aos<F>(p + 3 * F::N / 4, P.T);
+  }
+  __device__ static Acc ld(const uint4* p) {
+    Acc P;
+    P.X = ld_aos<F>(p);
+    P.Y = ld_aos<F>(p + F::N / 4);
+    P.Z = ld_aos<F>(p + 2 * F::N / 4);
+    P.T = ld_aos<F>(p + 3 * F::N / 4);
+    return P;
+  }
+  __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
+    const uint4* p = bases + (size_t)idx * (3 * F::N / 4);
+    Niels<F> Q;
+    Q.yp = ld_aos<F>(p);
+    Q.ym = ld_aos<F>(p + F::N / 4);
+    Q.kt = ld_aos<F>(p + 2 * F::N / 4);
+    return ext_add_niels<F>(a, Q, neg);
+  }
+  // (X/Z, Y/Z): src/bigint/twisted-edwards.ts:39-45; is_zero flags the neutral point (0, 1)
+  __device__ static void normalise(const Acc& a, uint32_t* out) {
+    Fe<F> zi = fe_inv(a.Z);
+    Fe<F> x = fe_from_mont(fe_mul(a.X, zi));
+    Fe<F> y = fe_from_mont(fe_mul(a.Y, zi));
+    bool zero = fe_is_zero(x);
+    for (int i = 0; i < F::N; i++) {
+      out[i] = x.v[i];
+      out[F::N + i] = y.v[i];
+      if (y.v[i] != (i == 0 ? 1u : 0u)) zero = false;
+    }
+    out[2 * F::N] = zero ? 1u : 0u;
+  }
+};
+
+// ---- level-0 loaders ----------------------------------------------------------------------
+// affine bucket sums left by the last round of the batched-affine tree
+template <class F, uint32_t B3>
+struct AffineBucketLoader {
+  ElemBuf<F> last;
+  const uint32_t* cnt;
+  const uint32_t* po_last;
+  __device__ __forceinline__ void add_bucket(Proj<F>& run, uint32_t b) const {
+    if (cnt[b] == 0) return;
+    Aff<F> A = last.load(2 * (size_t)po_last[b]);
+    if (!aff_is_inf(A)) run = proj_add_mixed<F, B3>(run, A);
+  }
+};
+
+// accumulators written by k_bucket_acc (basic bucket method)
+template <class C>
+struct AccBucketLoader {
+  const uint4* buckets;
+  __device__ __forceinline__ void add_bucket(typename C::Acc& run, uint32_t b) const {
+    run = C::add(run, C::ld(buckets + (size_t)b * (C::ACC_FE * C::F::N / 4)));
+  }
+};
+
+template <class C>
+__host__ __device__ constexpr int item_u4() {
+  return 2 * C::ACC_FE * C::F::N / 4;
+}
+
+template <class C, class Loader>
+__global__ void k_reduce0(Loader ld, uint32_t NB, int gb, uint4* __restrict__ out) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t g = 1u << gb;
+  if ((size_t)u * g >= NB) return;
+  typename C::Acc run = C::zero(), tri = C::zero();
+#pragma unroll 1
+  for (int jj = (int)g - 1; jj >= 0; jj--) {
+    ld.add_bucket(run, u * g + jj);
+    tri = C::add(tri, run);
+  }
+#pragma unroll 1
+  for (int d = 0; d < gb; d++) run = C::dbl(run);
+  uint4* o = out + (size_t)u * item_u4<C>();
+  C::st(o, run);
+  C::st(o + item_u4<C>() / 2, tri);
+}
+
+template <class C>
+__global__ void k_reduce_up(const uint4* __restrict__ in, uint32_t n_items, int gb, uint4* __restrict__ out) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t g = 1u << gb;
+  if ((size_t)u * g >= n_items) return;
+  typename C::Acc run = C::zero(), tri = C::zero(), xs = C::zero();
+#pragma unroll 1
+  for (int jj = (int)g - 1; jj >= 0; jj--) {
+    const uint4* p = in + (size_t)(u * g + jj) * item_u4<C>();
+    xs = C::add(xs, C::ld(p + item_u4<C>() / 2));
+    run = C::add(run, C::ld(p));
+    if (jj > 0) tri = C::add(tri, run);
+  }
+#pragma unroll 1
+  for (int d = 0; d < gb; d++) run = C::dbl(run);
+  uint4* o = out + (size_t)u * item_u4<C>();
+  C::st(o, run);
+  C::st(o + item_u4<C>() / 2, C::add(tri, xs));
+}
+
+template <class C>
+__global__ void k_horner(const uint4* __restrict__ items, int K, int c, uint4* __restrict__ partial) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename C::Acc acc = C::ld(items + (size_t)(K - 1) * item_u4<C>() + item_u4<C>() / 2);
+#pragma unroll 1
+  for (int k = K - 2; k >= 0; k--) {
+#pragma unroll 1
+    for (int d = 0; d < c; d++) acc = C::dbl(acc);
+    acc = C::add(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
+  }
+  C::st(partial, acc);
+}
+
+template <class C>
+__global__ void k_zero_partial(uint4* __restrict__ partial) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) C::st(partial, C::zero());
+}
+
+// Sum `count` partials and normalise (Projective.toAffine + fromMontgomery,
+// src/curve-projective.ts:335-349, src/field-msm.ts:182-185).
+template <class C>
+__global__ void k_finalize(const uint4* __restrict__ partials, int count, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename C::Acc acc = C::ld(partials);
+#pragma unroll 1
+  for (int i = 1; i < count; i++) acc = C::add(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
+  C::normalise(acc, out);
+}
+
+}  // namespace msm

@@ -1,0 +1,203 @@
+"""MsmEngine: one GPU + one curve behind the C ABI (include/msm_b200.h).
+
+Host buffers are numpy arrays / bytes in one of the two boundary layouts:
+  * LIMB29_MONT -- the reference's in-memory format (src/curve-affine.ts:20-52,
+    src/scalar-glv.ts:60-66): what `Parallel.msm(scalarPtr, pointPtr, N)` reads from wasm memory
+  * LE_BYTES    -- the compute_msm wire format (src/parallel.ts:97-133,209-249)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+CURVES = {"bls12-377": L.CURVE_BLS12_377_G1, "pallas": L.CURVE_PALLAS,
+          "ed-on-bls12-377": L.CURVE_ED_ON_BLS12_377}
+FIELD_BYTES = {L.CURVE_BLS12_377_G1: 48, L.CURVE_PALLAS: 32, L.CURVE_ED_ON_BLS12_377: 32}
+
+
+@dataclass
+class MsmResult:
+    x: int
+    y: int
+    is_zero: bool
+    timing: dict
+
+
+def _as_buffer(a) -> Tuple[C.c_void_p, object]:
+    """Returns (pointer, keepalive) for bytes / bytearray / numpy input without copying numpy."""
+    if isinstance(a, np.ndarray):
+        a = np.ascontiguousarray(a)
+        return C.c_void_p(a.ctypes.data), a
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(a, dtype=np.uint8)
+        return C.c_void_p(arr.ctypes.data), arr
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+class PinnedBuffer:
+    """Page-locked host memory (the analogue of the SharedArrayBuffer the N-API addon reads)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        L.check(L.lib().msm_b200_host_alloc_pinned(C.byref(self.ptr), nbytes))
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(max(nbytes, 1),))[:nbytes]
+
+    def free(self):
+        if self.ptr:
+            L.lib().msm_b200_host_free_pinned(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MsmEngine:
+    def __init__(self, curve: str | int, device: int = 0, stream: Optional[int] = None):
+        self.curve = CURVES[curve] if isinstance(curve, str) else int(curve)
+        self.device = device
+        self._ctx = C.c_void_p()
+        self._lib = L.lib()
+        L.check(self._lib.msm_b200_create(C.byref(self._ctx), self.curve, device, C.c_void_p(stream or 0)))
+        self.field_bytes = FIELD_BYTES[self.curve]
+        self.default_form = L.FORM_TE_EXTENDED if self.curve == L.CURVE_ED_ON_BLS12_377 else L.FORM_AFFINE_GLV
+
+    # -- lifecycle
+    def close(self):
+        if self._ctx:
+            self._lib.msm_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- sizes
+    def point_bytes(self, layout: int) -> int:
+        return self._lib.msm_b200_point_bytes(self._ctx, layout)
+
+    def scalar_bytes(self, layout: int) -> int:
+        return self._lib.msm_b200_scalar_bytes(self._ctx, layout)
+
+    def partial_bytes(self) -> int:
+        return self._lib.msm_b200_partial_bytes(self._ctx)
+
+    # -- inputs
+    def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
+        ptr, keep = _as_buffer(points)
+        L.check(self._lib.msm_b200_set_bases(self._ctx, ptr, n, layout, 0), self._ctx)
+
+    def set_bases_device(self, dev_ptr: int, n: int, layout: int = L.LAYOUT_LE_BYTES):
+        L.check(self._lib.msm_b200_set_bases(self._ctx, C.c_void_p(dev_ptr), n, layout, 1), self._ctx)
+
+    # -- the MSM
+    def _result(self, pt: L.Point, tm: L.Timing) -> MsmResult:
+        x = int.from_bytes(bytes(pt.x), "little")
+        y = int.from_bytes(bytes(pt.y), "little")
+        return MsmResult(x, y, bool(pt.is_zero), tm.as_dict())
+
+    def run(self, scalars, n: int, layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None,
+            window_bits: int = 0, on_device: bool = False) -> MsmResult:
+        pt, tm = L.Point(), L.Timing()
+        if on_device:
+            ptr, keep = C.c_void_p(int(scalars)), None
+        else:
+            ptr, keep = _as_buffer(scalars)
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_run(self._ctx, ptr, n, layout, int(on_device), form, window_bits,
+                                       C.byref(pt), C.byref(tm)), self._ctx)
+        return self._result(pt, tm)
+
+    def msm(self, scalars, points, n: int, scalar_layout: int = L.LAYOUT_LE_BYTES,
+            point_layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None, window_bits: int = 0) -> MsmResult:
+        pt, tm = L.Point(), L.Timing()
+        sp, k1 = _as_buffer(scalars)
+        pp, k2 = _as_buffer(points)
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_msm(self._ctx, sp, scalar_layout, pp, point_layout, n, form, window_bits,
+                                       C.byref(pt), C.byref(tm)), self._ctx)
+        return self._result(pt, tm)
+
+    def run_partial(self, scalars, n: int, partial_dev_ptr: int, layout: int = L.LAYOUT_LE_BYTES,
+                    form: Optional[int] = None, window_bits: int = 0, on_device: bool = False) -> dict:
+        tm = L.Timing()
+        if on_device:
+            ptr, keep = C.c_void_p(int(scalars)), None
+        else:
+            ptr, keep = _as_buffer(scalars)
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_run_partial(self._ctx, ptr, n, layout, int(on_device), form, window_bits,
+                                               C.c_void_p(partial_dev_ptr), C.byref(tm)), self._ctx)
+        return tm.as_dict()
+
+    def combine(self, partials_dev_ptr: int, count: int) -> MsmResult:
+        pt = L.Point()
+        L.check(self._lib.msm_b200_combine(self._ctx, C.c_void_p(partials_dev_ptr), count, C.byref(pt)), self._ctx)
+        return self._result(pt, L.Timing())
+
+    # -- device memory / generators
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        L.check(self._lib.msm_b200_dev_alloc(self._ctx, C.byref(p), nbytes), self._ctx)
+        return p.value
+
+    def dev_free(self, ptr: int):
+        L.check(self._lib.msm_b200_dev_free(self._ctx, C.c_void_p(ptr)), self._ctx)
+
+    def d2h(self, dev_ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        L.check(self._lib.msm_b200_memcpy_d2h(self._ctx, C.c_void_p(out.ctypes.data), C.c_void_p(dev_ptr), nbytes),
+                self._ctx)
+        return out
+
+    def h2d(self, dev_ptr: int, host) -> None:
+        ptr, keep = _as_buffer(host)
+        L.check(self._lib.msm_b200_memcpy_h2d(self._ctx, C.c_void_p(dev_ptr), ptr, keep.nbytes), self._ctx)
+
+    def random_points_device(self, dev_ptr: int, n: int, seed: int):
+        L.check(self._lib.msm_b200_random_points(self._ctx, C.c_void_p(dev_ptr), n, seed), self._ctx)
+
+    def random_scalars_device(self, dev_ptr: int, n: int, seed: int):
+        L.check(self._lib.msm_b200_random_scalars(self._ctx, C.c_void_p(dev_ptr), n, seed), self._ctx)
+
+    # -- test hooks
+    def test_digits(self, scalars_le: bytes, n: int, window_bits: int) -> np.ndarray:
+        kmax = 2 * n * 128
+        out = np.zeros(kmax, dtype=np.uint32)
+        K = C.c_int()
+        ptr, keep = _as_buffer(scalars_le)
+        L.check(self._lib.msm_b200_test_digits(self._ctx, ptr, n, window_bits, C.c_void_p(out.ctypes.data),
+                                               C.byref(K)), self._ctx)
+        return out[: 2 * n * K.value].reshape(2 * n, K.value)
+
+
+def test_field_op(device: int, field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    out = np.empty_like(a)
+    L.check(L.lib().msm_b200_test_field_op(device, field, op, C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data),
+                                           C.c_void_p(out.ctypes.data), a.shape[0]))
+    return out
+
+
+def microbench(device: int, which: int, iters: int = 64) -> Tuple[float, float]:
+    ops = C.c_double()
+    ms = C.c_float()
+    L.check(L.lib().msm_b200_microbench(device, which, iters, C.byref(ops), C.byref(ms)))
+    return ops.value, ms.value

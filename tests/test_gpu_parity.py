@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle on the same inputs.
+Bit-exact (integer work): normalised affine output must be identical
+(src/msm.test.ts:65-82,115-118; scripts/msm-weierstrass.ts:97-107)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bigint_oracle as O
+from tests import inputs as I
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mz():
+    import msm_zprize_b200 as m
+    return m
+
+
+FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8)}
+
+
+def _limbs(vals, n):
+    return np.array([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)] for v in vals], dtype=np.uint32)
+
+
+def _vals(arr):
+    return [sum(int(w) << (32 * i) for i, w in enumerate(row)) for row in arr]
+
+
+@pytest.mark.parametrize("field", [0, 1, 2])
+def test_field_ops_on_device(mz, field):
+    # src/field.test.ts:15-155 -- multiply / add / subtract / inverse against BigInt
+    from msm_zprize_b200.engine import test_field_op
+    p, n = FIELDS[field]
+    R = 1 << (32 * n)
+    Ri = pow(R, -1, p)
+    rng = random.Random(field)
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, R % p]
+    a = edge + [rng.randrange(p) for _ in range(505)]
+    b = [rng.randrange(p) for _ in range(len(a) - 7)] + edge
+    A, B = _limbs(a, n), _limbs(b, n)
+    assert _vals(test_field_op(0, field, 0, A, B)) == [x * y * Ri % p for x, y in zip(a, b)]
+    assert _vals(test_field_op(0, field, 1, A, B)) == [(x + y) % p for x, y in zip(a, b)]
+    assert _vals(test_field_op(0, field, 2, A, B)) == [(x - y) % p for x, y in zip(a, b)]
+    nz = [x if x else 1 for x in a][:64]
+    assert _vals(test_field_op(0, field, 3, _limbs(nz, n), _limbs(nz, n))) == [pow(x, -1, p) * R * R % p for x in nz]
+
+
+@pytest.mark.parametrize("name,params,c", [("bls12-377", O.BLS12_377, 13), ("pallas", O.PALLAS, 7),
+                                           ("bls12-377", O.BLS12_377, 16)])
+def test_glv_digits_on_device(mz, name, params, c):
+    # src/glv/glv-test.ts:83-125 + src/msm-batched-affine.ts:178-191, digit by digit
+    g = O.glv_params(params.q, params.lam)
+    n = 300
+    sc = [0, 1, params.q - 1, params.lam] + O.random_scalars(n - 4, params.q, seed=5)
+    with mz.MsmEngine(name) as eng:
+        dig = eng.test_digits(I.scalars_le(sc), n, c)
+    K = -(-(g.max_bits + 1) // c)
+    assert dig.shape == (2 * n, K)
+    for i, s in enumerate(sc):
+        halves = O.glv_decompose(s, g)
+        for j, h in enumerate(halves):
+            want = O.signed_digits(abs(h), c, K)
+            for k, (l, carry) in enumerate(want):
+                neg = (carry ^ (1 if h < 0 else 0)) if l else 0
+                assert int(dig[2 * i + j, k]) == (l | (neg << 31)), (i, j, k)
+
+
+def _check_weierstrass(mz, name, params, scalars, points, layout="le", form=None, c=0, unreduced=None):
+    aff = O.WeierstrassAffine(params)
+    n = len(scalars)
+    nb = 48 if name == "bls12-377" else 32
+    want = O.msm(aff, scalars, points) if n else None
+    with mz.MsmEngine(name) as eng:
+        if layout == "le":
+            assert all(P is not None for P in points)
+            res = eng.msm(I.scalars_le(scalars), I.points_le(points, nb), n, mz.LAYOUT_LE_BYTES, mz.LAYOUT_LE_BYTES,
+                          form=form, window_bits=c)
+        else:
+            res = eng.msm(I.scalars_limb29(scalars, params.q), I.points_limb29(points, params.p, unreduced), n,
+                          mz.LAYOUT_LIMB29_MONT, mz.LAYOUT_LIMB29_MONT, form=form, window_bits=c)
+    if want is None:
+        assert res.is_zero and res.x == 0 and res.y == 0
+    else:
+        assert not res.is_zero
+        assert (res.x, res.y) == want
+    return res
+
+
+KAT_BLS_P = (
+    111871295567327857271108656266735188604298176728428155068227918632083036401841336689521497731900230387779623820740,
+    76860045326390600098227152997486448974650822224305058012700629806287380625419427989664237630603922765089083164740,
+)
+KAT_ED_P = (
+    2796670805570508460920584878396618987767121022598342527208237783066948667246,
+    8134280397689638111748378379571739274369602049665521098046934931245960532166,
+)
+
+
+def test_kat_bls12_377(mz):
+    # scripts/zprize23/submission-test-bls377.ts:18-45
+    q = O.BLS12_377.q
+    res = _check_weierstrass(mz, "bls12-377", O.BLS12_377, [2, q - 1], [KAT_BLS_P, KAT_BLS_P])
+    assert (res.x, res.y) == KAT_BLS_P
+    rng = random.Random(1)
+    sc = [rng.randrange(q) for _ in range(1000)]
+    aff = O.WeierstrassAffine(O.BLS12_377)
+    with mz.MsmEngine("bls12-377") as eng:
+        r2 = eng.msm(I.scalars_le(sc), I.points_le([KAT_BLS_P] * 1000, 48), 1000)
+    assert (r2.x, r2.y) == aff.scale(sum(sc) % q, KAT_BLS_P)
+
+
+@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 16, 64, 257, 1024])
+def test_msm_weierstrass_sizes(mz, name, params, n):
+    # src/msm.test.ts:35-83: N = 2^0 .. 2^12 (the oracle here is python: up to 2^10)
+    aff = O.WeierstrassAffine(params)
+    pts = O.random_points_weierstrass(aff, n, seed=n)
+    sc = O.random_scalars(n, params.q, seed=1000 + n)
+    _check_weierstrass(mz, name, params, sc, pts, "le")
+    if n <= 64:
+        _check_weierstrass(mz, name, params, sc, pts, "limb29", unreduced=[i % 2 == 1 for i in range(n)])
+        _check_weierstrass(mz, name, params, sc, pts, "le", form=mz.FORM_PROJECTIVE)
+
+
+@pytest.mark.parametrize("c", [1, 2, 5, 9, 14, 16])
+def test_window_size_invariance(mz, c):
+    # any c gives the same point (src/msm-batched-affine.ts:79-98 options.c)
+    aff = O.WeierstrassAffine(O.BLS12_377)
+    n = 40
+    pts = O.random_points_weierstrass(aff, n, seed=77)
+    sc = O.random_scalars(n, aff.q, seed=78)
+    _check_weierstrass(mz, "bls12-377", O.BLS12_377, sc, pts, "le", c=c)
+    _check_weierstrass(mz, "bls12-377", O.BLS12_377, sc, pts, "le", c=c, form=mz.FORM_PROJECTIVE)
+
+
+def test_edge_cases_safe_additions(mz):
+    # batchAddNew semantics (src/curve-affine.ts:376-458): doubling, P + (-P), zero points,
+    # scalars 0 / 1 / q-1; src/bigint/msm.test.ts:35-57 identities
+    params = O.BLS12_377
+    aff = O.WeierstrassAffine(params)
+    q = params.q
+    pts = O.random_points_weierstrass(aff, 8, seed=3)
+    P, Q = pts[0], pts[1]
+    # all-equal points with equal scalars: every pair is a doubling
+    _check_weierstrass(mz, "bls12-377", params, [5] * 16, [P] * 16, c=4)
+    # P and -P with the same scalar: cancels to zero
+    _check_weierstrass(mz, "bls12-377", params, [7, 7], [P, aff.negate(P)], c=4)
+    _check_weierstrass(mz, "bls12-377", params, [7, 7, 9], [P, aff.negate(P), Q], c=4)
+    # zero / one / q-1 scalars
+    _check_weierstrass(mz, "bls12-377", params, [0, 0, 0], pts[:3])
+    _check_weierstrass(mz, "bls12-377", params, [0, 1, q - 1, 2], [P, Q, Q, P])
+    # zero points in the reference's in-memory layout (isNonZero flag = 0)
+    _check_weierstrass(mz, "bls12-377", params, [3, 4, 5, 6], [P, None, Q, None], layout="limb29")
+    _check_weierstrass(mz, "bls12-377", params, [3, 4], [None, None], layout="limb29")
+    # empty input
+    _check_weierstrass(mz, "bls12-377", params, [], [])
+
+
+def _check_te(mz, scalars, points, layout="le", c=0):
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    n = len(scalars)
+    want = te.to_affine(O.msm(te, scalars, [te.from_affine(P) for P in points])) if n else (0, 1)
+    with mz.MsmEngine("ed-on-bls12-377") as eng:
+        if layout == "le":
+            res = eng.msm(I.scalars_le(scalars), I.points_le(points, 32), n, window_bits=c)
+        else:
+            res = eng.msm(I.scalars_limb29(scalars, te.q), I.te_points_limb29(points, te.p), n,
+                          mz.LAYOUT_LIMB29_MONT, mz.LAYOUT_LIMB29_MONT, window_bits=c)
+    assert (res.x, res.y) == want
+    assert res.is_zero == (want == (0, 1))
+    return res
+
+
+def test_kat_ed_on_bls12_377(mz):
+    # scripts/zprize23/submission-test.ts:13-21
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    res = _check_te(mz, [2, te.q - 1], [KAT_ED_P, KAT_ED_P])
+    assert (res.x, res.y) == KAT_ED_P
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 64, 300, 1024])
+def test_msm_twisted_edwards_sizes(mz, n):
+    # src/msm.test.ts:94-119
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    pts = O.random_points_te(te, n, seed=n)
+    sc = O.random_scalars(n, te.q, seed=2000 + n)
+    _check_te(mz, sc, pts, "le")
+    if n <= 64:
+        _check_te(mz, sc, pts, "limb29", c=5)
+
+
+def test_te_edge_cases(mz):
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    pts = O.random_points_te(te, 4, seed=9)
+    P = pts[0]
+    negP = te.to_affine(te.negate(te.from_affine(P)))
+    _check_te(mz, [5] * 8, [P] * 8, c=3)
+    _check_te(mz, [7, 7], [P, negP], c=3)
+    _check_te(mz, [0, 0], pts[:2])
+    _check_te(mz, [], [])
+
+
+def test_error_behaviour(mz):
+    # errors are codes + messages, never a crash (the reference throws: src/util.ts:256)
+    with mz.MsmEngine("bls12-377") as eng:
+        with pytest.raises(mz.MsmError):
+            eng.run(b"\0" * 32, 1)  # run before set_bases
+        with pytest.raises(mz.MsmError):
+            eng.msm(b"\0" * 32, b"\0" * 96, 1, form=mz.FORM_TE_EXTENDED)
+        with pytest.raises(mz.MsmError):
+            eng.msm(b"\0" * 32, b"\0" * 96, 1, window_bits=99)
+    with pytest.raises(mz.MsmError):
+        mz.MsmEngine("bls12-377", device=99)
+
+
+def test_resident_bases_and_fresh_scalars(mz):
+    # benchmark shape of scripts/msm-weierstrass.ts:12-51: bases fixed, new scalars per run
+    params = O.BLS12_377
+    aff = O.WeierstrassAffine(params)
+    n = 128
+    pts = O.random_points_weierstrass(aff, n, seed=42)
+    with mz.MsmEngine("bls12-377") as eng:
+        eng.set_bases(I.points_le(pts, 48), n)
+        for it in range(3):
+            sc = O.random_scalars(n, params.q, seed=500 + it)
+            res = eng.run(I.scalars_le(sc), n)
+            assert (res.x, res.y) == O.msm(aff, sc, pts)
+        # prefix of the resident bases
+        sc = O.random_scalars(50, params.q, seed=600)
+        res = eng.run(I.scalars_le(sc), 50)
+        assert (res.x, res.y) == O.msm(aff, sc, pts[:50])
