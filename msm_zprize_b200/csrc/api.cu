@@ -358,6 +358,7 @@ int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, f
       case 1: k_mb_imad<1><<<blocks, threads>>>(d, iters, 12345u); break;
       case 2: k_mb_imad<2><<<blocks, threads>>>(d, iters, 12345u); break;
       case 5: k_mb_imad<5><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 8: k_mb_imad<8><<<blocks, threads>>>(d, iters, 12345u); break;
       case 3: k_mb_modmul<Bls377Fq><<<blocks, threads>>>(d, iters, 12345u); break;
       case 4: k_mb_modmul<PallasFp><<<blocks, threads>>>(d, iters, 12345u); break;
       default: cudaFree(d); return fail(nullptr, MSM_E_INVALID, "unknown benchmark");

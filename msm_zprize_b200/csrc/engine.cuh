@@ -208,6 +208,9 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
   return 0;
 }
 
+template <class C>
+static int zero_partial_t(msm_b200_ctx* ctx);
+
 // ------------------------------------------------------------------------------------------
 // bucket reduction + Horner -> partial result in ctx->partial (any curve form)
 // ------------------------------------------------------------------------------------------
@@ -396,6 +399,14 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     return 0;
   }
   unsigned long long n_adds = 0;
+  if (P0 == 0) {  // every digit is zero (e.g. all scalars are 0): the sum is the neutral element
+    RET_IF((zero_partial_t<WeierCurve<F, B3>>(ctx)));
+    if (tm) {
+      tm->window_bits = c;
+      tm->n_windows = K;
+    }
+    return 0;
+  }
   // --- scatter
   RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
   RET_IF(ensure(ctx, ctx->pairkey[0], (P0 + 1) * 4));

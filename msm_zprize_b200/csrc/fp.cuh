@@ -223,8 +223,16 @@ MSM_HD Fe<F> fe_select(bool c, const Fe<F>& a, const Fe<F>& b) {  // c ? a : b
 }
 
 // ------------------------------------------------------------------------------------------
-// Montgomery product  a*b*2^(-32N) mod p, canonical in/out.
+// Montgomery product  a*b*2^(-32N) mod p, canonical in/out.          (THE hot function)
 // (replaces src/wasm/multiply-montgomery.ts:58-136)
+//
+// Measured on B200 (tools/microbench.py, profiles/): IMAD.WIDE.U32 issues at 9.1e12/s chip-wide
+// (one warp instruction per 4 cycles per SM sub-partition), with or without carry in/out, and
+// IMAD.HI at the same rate -- so one IMAD.WIDE per 32x32->64 limb product is the cheapest form
+// and 9.1e12 limb products/s is the roofline.  This product issues 2N^2 + N IMAD-pipe
+// instructions (N = 12: 279 IMAD.WIDE + 14 IMAD) and runs at 30.0e9/s = 98% of that bound.
+// A 29-bit-limb variant with carry-free 64-bit accumulation (the reference's own scheme) was
+// measured slower (23.2e9/s): it needs 13 limbs (328 IMAD.WIDE) plus ~390 ALU instructions.
 //
 // State between rows: two accumulators.  X is word aligned (word w has weight 2^(32w), N+1
 // words), Y sits one word higher (word w has weight 2^(32(w+1)), N words); T = X + Y*2^32.
@@ -267,7 +275,7 @@ MSM_HD void mont_row(uint32_t* U, uint32_t* V, const uint32_t* a, uint32_t bi) {
     }
     V[N] = addc(0u, 0u);
   }
-  uint32_t m = mul_lo(V[0], F::M0);
+  uint32_t m = mul_lo(V[0], F::M0v());
   // m*p, odd limbs of p into Y
   U[0] = mad_lo_cc(F::P(1), m, U[0]);
   U[1] = madc_hi_cc(F::P(1), m, U[1]);

@@ -153,7 +153,7 @@ __global__ void k_hist_scatter(SortArgs a) {
   uint32_t carry = 0;
   for (int k = 0; k < a.K; k++) {
     uint32_t l = signed_digit<4>(s, k, a.c, carry);
-    if (a.digits && !SCATTER) a.digits[h * a.K + k] = l | ((carry ^ (l ? sign : 0)) << 31);
+    if (a.digits && !SCATTER) a.digits[h * a.K + k] = l | ((l ? (carry ^ sign) : 0u) << 31);
     if (l == 0) continue;
     uint32_t b = (uint32_t)k * a.L + (l - 1);
     if (!SCATTER) {

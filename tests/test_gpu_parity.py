@@ -19,6 +19,8 @@ def mz():
 
 
 FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8)}
+# internal Montgomery radix R = 2^(32 N)  (fp.cuh fe_mul)
+RBITS = {0: 384, 1: 256, 2: 256}
 
 
 def _limbs(vals, n):
@@ -34,7 +36,7 @@ def test_field_ops_on_device(mz, field):
     # src/field.test.ts:15-155 -- multiply / add / subtract / inverse against BigInt
     from msm_zprize_b200.engine import test_field_op
     p, n = FIELDS[field]
-    R = 1 << (32 * n)
+    R = 1 << RBITS[field]
     Ri = pow(R, -1, p)
     rng = random.Random(field)
     edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, R % p]
