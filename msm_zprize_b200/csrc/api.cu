@@ -136,7 +136,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
     }
     ctx->own_stream = true;
   }
-  cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, (MAX_ROUNDS + 2) * 8);
+  cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, (MAX_ROUNDS + 3) * 8);
   cudaError_t e2 = cudaMallocHost((void**)&ctx->h_result, 64 * 4);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     delete ctx;

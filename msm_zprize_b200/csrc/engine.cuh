@@ -140,22 +140,16 @@ static size_t point_bytes(int curve, int layout) {
 }
 static size_t scalar_bytes(int layout) { return layout == MSM_LAYOUT_LE_BYTES ? 32 : 36; }
 
-// engine default window size (the reference's table is tuned for 16 CPU threads,
-// src/msm-common.ts:33-57; any c gives the same result)
+// Engine default window size (the reference's table is tuned for 16 CPU threads,
+// src/msm-common.ts:33-57; any c gives the same result).  The GPU wants windows that divide the
+// scalar length evenly -- a short top window concentrates all its entries in a few buckets and
+// costs extra tree rounds -- so: GLV halves (127/128 bits) use c = 16 (K = 8) from 2^14 points up,
+// full-width scalars (252..256 bits) c = 14 / 16 / 18.
 static int default_window(int curve, int form, size_t n) {
   int lg = ceil_log2_sz(n);
-  int c;
-  if (form == MSM_FORM_AFFINE_GLV) {
-    c = lg - 5;
-    if (c < 4) c = 4;
-    if (c > 16) c = 16;
-  } else {
-    c = lg - 6;
-    if (c < 4) c = 4;
-    if (c > 16) c = 16;
-  }
-  (void)curve;
-  return c;
+  if (form == MSM_FORM_AFFINE_GLV) return lg >= 14 ? 16 : (lg >= 7 ? 8 : 4);
+  if (curve == MSM_CURVE_ED_ON_BLS12_377) return lg >= 21 ? 18 : (lg >= 13 ? 14 : (lg >= 7 ? 9 : 4));
+  return lg >= 13 ? 16 : (lg >= 7 ? 8 : 4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -259,7 +253,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
   RET_IF(ensure(ctx, ctx->po, NB * 4));
-  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 2) * 8));
+  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 3) * 8));
   LAUNCH(ctx, k_load_scalars<S>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
@@ -277,9 +271,10 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.digits = nullptr;
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
+  CK(cudaMemsetAsync(ctx->totals.p, 0, (MAX_ROUNDS + 3) * 8, ctx->stream));
   LAUNCH(ctx, k_scan, 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
          (unsigned long long*)ctx->totals.p);
-  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t P0 = ctx->h_totals[0];
   RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
@@ -308,7 +303,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
     tm->window_bits = c;
     tm->n_windows = K;
     tm->rounds = 0;
-    tm->n_adds = 0;  // filled by the caller from the histogram if needed
+    tm->n_adds = ctx->h_totals[MAX_ROUNDS + 2];  // one mixed addition per sorted entry
   }
   return 0;
 }
@@ -363,7 +358,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
   RET_IF(ensure(ctx, ctx->po, (size_t)(MAX_ROUNDS + 1) * NB * 4));
-  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 2) * 8));
+  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 3) * 8));
   LAUNCH(ctx, k_glv<G>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
@@ -382,9 +377,10 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
   int e1 = T.mark();
   // --- offsets for every round, one host sync
+  CK(cudaMemsetAsync(ctx->totals.p, 0, (MAX_ROUNDS + 3) * 8, ctx->stream));
   LAUNCH(ctx, k_scan, MAX_ROUNDS + 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
          (unsigned long long*)ctx->totals.p);
-  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const unsigned long long maxcnt = ctx->h_totals[MAX_ROUNDS + 1];
   int R = 1;
@@ -458,7 +454,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
       LAUNCH(ctx, (k_bwd<F, false>), grid, ACC_THREADS, a);
     int h1 = T.mark();
     hot.push_back({h0, h1});
-    n_adds += P;  // upper bound: includes pass-through singles
+    n_adds += (r == 0 ? ctx->h_totals[MAX_ROUNDS + 2] : ctx->h_totals[r - 1]) - P;  // elements - pairs
   }
   CK(cudaGetLastError());
   int e3 = T.mark();

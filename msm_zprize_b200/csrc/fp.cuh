@@ -341,9 +341,10 @@ MSM_HD Fe<F> fe_mul_small(const Fe<F>& a, uint32_t c) {
 }
 
 // Montgomery-domain inverse by Fermat: a^(p-2)   (a = x*R  ->  x^-1 * R).  a != 0.
-// Fixed 4-bit windows over the exponent p-2 (replaces src/wasm/inverse.ts:191-218).
+// Fixed 4-bit windows over the exponent p-2.  Kept as the independent cross-check of fe_inv
+// (tests/test_hostmath.py); ~480 dependent Montgomery products = ~0.3 ms for a lone warp.
 template <class F>
-MSM_HD Fe<F> fe_inv(const Fe<F>& a) {
+MSM_HD Fe<F> fe_inv_fermat(const Fe<F>& a) {
   Fe<F> tbl[16];
   tbl[0] = fe_one<F>();
   tbl[1] = a;
@@ -366,6 +367,188 @@ MSM_HD Fe<F> fe_inv(const Fe<F>& a) {
     }
   }
   return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Montgomery-domain inverse, a = x*R -> x^-1 * R  (a != 0): variable-time "safegcd" divsteps
+// (Bernstein-Yang 2019) in batches of 30 on signed 30-bit limbs, followed by one Montgomery
+// product with R^3.  Replaces the reference's Kaliski almost-inverse + fix-up
+// (src/wasm/inverse.ts:42-218).  ~27 batches of (30 divsteps on the low words + two linear
+// updates of L30 limbs) instead of ~480 dependent field multiplications: this is what sits on the
+// critical path of every batched-affine round (one true inversion per product tree).
+// ------------------------------------------------------------------------------------------
+MSM_HD int msm_ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+
+template <class F>
+struct Inv30 {
+  static constexpr int L = (F::BITS + 2 + 29) / 30;  // limbs: values range over (-2p, p)
+  static constexpr int32_t M30 = 0x3FFFFFFF;
+  int32_t v[L];
+};
+
+template <class F>
+MSM_HD int32_t inv30_modulus_limb(int i) {  // bits [30i, 30i+30) of p
+  const int bit = 30 * i, k = bit >> 5, sh = bit & 31;
+  uint32_t lo = (k < F::N) ? (F::P(k) >> sh) : 0u;
+  if (sh > 2 && k + 1 < F::N) lo |= F::P(k + 1) << (32 - sh);
+  return (int32_t)(lo & 0x3FFFFFFFu);
+}
+
+template <class F>
+MSM_HD Fe<F> fe_inv_plain(const Fe<F>& x) {  // x^-1 mod p as plain integers, x in [1, p)
+  typedef Inv30<F> I;
+  constexpr int L = I::L;
+  constexpr int32_t M30 = I::M30;
+  int32_t P30[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) P30[i] = inv30_modulus_limb<F>(i);
+  // p^-1 mod 2^30 by Newton iteration on the low word
+  uint32_t pinv = P30[0];
+#pragma unroll
+  for (int i = 0; i < 5; i++) pinv *= 2u - (uint32_t)P30[0] * pinv;
+  pinv &= (uint32_t)M30;
+
+  int32_t d[L], e[L], f[L], g[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    d[i] = 0;
+    e[i] = 0;
+    f[i] = P30[i];
+    const int bit = 30 * i, k = bit >> 5, sh = bit & 31;
+    uint32_t lo = (k < F::N) ? (x.v[k] >> sh) : 0u;
+    if (sh > 2 && k + 1 < F::N) lo |= x.v[k + 1] << (32 - sh);
+    g[i] = (int32_t)(lo & (uint32_t)M30);
+  }
+  e[0] = 1;
+  int32_t eta = -1;
+#pragma unroll 1
+  for (int iter = 0; iter < 64; iter++) {
+    // ---- 30 divsteps on the low 32 bits of f, g -> transition matrix (u v; q r)
+    uint32_t u = 1, v = 0, q = 0, r = 1;
+    uint32_t f0 = (uint32_t)f[0] | ((uint32_t)f[1] << 30), g0 = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
+    int i = 30;
+#pragma unroll 1
+    for (;;) {
+      int zeros = msm_ctz32(g0 | (0xFFFFFFFFu << i));
+      g0 >>= zeros;
+      u <<= zeros;
+      v <<= zeros;
+      eta -= zeros;
+      i -= zeros;
+      if (i == 0) break;
+      if (eta < 0) {
+        uint32_t t;
+        eta = -eta;
+        t = f0, f0 = g0, g0 = 0u - t;
+        t = u, u = q, q = 0u - t;
+        t = v, v = r, r = 0u - t;
+      }
+      int limit = (eta + 1) > i ? i : (eta + 1);
+      uint32_t m = (0xFFFFFFFFu >> (32 - limit)) & 63u;
+      uint32_t w = (f0 * g0 * (f0 * f0 - 2u)) & m;  // -g/f mod 2^min(limit,6)
+      g0 += f0 * w;
+      q += u * w;
+      r += v * w;
+    }
+    const int32_t su = (int32_t)u, sv = (int32_t)v, sq = (int32_t)q, sr = (int32_t)r;
+    // ---- (d, e) <- (u v; q r) (d, e) / 2^30 mod p
+    {
+      int32_t sd = d[L - 1] >> 31, se = e[L - 1] >> 31;
+      int32_t md = (su & sd) + (sv & se), me = (sq & sd) + (sr & se);
+      int64_t cd = (int64_t)su * d[0] + (int64_t)sv * e[0];
+      int64_t ce = (int64_t)sq * d[0] + (int64_t)sr * e[0];
+      md -= (int32_t)((pinv * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+      me -= (int32_t)((pinv * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+      cd += (int64_t)P30[0] * md;
+      ce += (int64_t)P30[0] * me;
+      cd >>= 30;
+      ce >>= 30;
+#pragma unroll
+      for (int k = 1; k < L; k++) {
+        cd += (int64_t)su * d[k] + (int64_t)sv * e[k];
+        ce += (int64_t)sq * d[k] + (int64_t)sr * e[k];
+        cd += (int64_t)P30[k] * md;
+        ce += (int64_t)P30[k] * me;
+        d[k - 1] = (int32_t)cd & M30;
+        cd >>= 30;
+        e[k - 1] = (int32_t)ce & M30;
+        ce >>= 30;
+      }
+      d[L - 1] = (int32_t)cd;
+      e[L - 1] = (int32_t)ce;
+    }
+    // ---- (f, g) <- (u v; q r) (f, g) / 2^30
+    {
+      int64_t cf = (int64_t)su * f[0] + (int64_t)sv * g[0];
+      int64_t cg = (int64_t)sq * f[0] + (int64_t)sr * g[0];
+      cf >>= 30;
+      cg >>= 30;
+#pragma unroll
+      for (int k = 1; k < L; k++) {
+        cf += (int64_t)su * f[k] + (int64_t)sv * g[k];
+        cg += (int64_t)sq * f[k] + (int64_t)sr * g[k];
+        f[k - 1] = (int32_t)cf & M30;
+        cf >>= 30;
+        g[k - 1] = (int32_t)cg & M30;
+        cg >>= 30;
+      }
+      f[L - 1] = (int32_t)cf;
+      g[L - 1] = (int32_t)cg;
+    }
+    int32_t nz = 0;
+#pragma unroll
+    for (int k = 0; k < L; k++) nz |= g[k];
+    if (nz == 0) break;
+  }
+  // f = +-1 now; result = sign(f) * d, normalised to [0, p)
+  {
+    int32_t sign = f[L - 1];
+    int32_t cond_add = d[L - 1] >> 31;
+    int32_t cond_neg = sign >> 31;
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+      d[k] += P30[k] & cond_add;
+      d[k] = (d[k] ^ cond_neg) - cond_neg;
+    }
+#pragma unroll
+    for (int k = 0; k < L - 1; k++) {
+      d[k + 1] += d[k] >> 30;
+      d[k] &= M30;
+    }
+    cond_add = d[L - 1] >> 31;
+#pragma unroll
+    for (int k = 0; k < L; k++) d[k] += P30[k] & cond_add;
+#pragma unroll
+    for (int k = 0; k < L - 1; k++) {
+      d[k + 1] += d[k] >> 30;
+      d[k] &= M30;
+    }
+  }
+  Fe<F> out;
+#pragma unroll
+  for (int k = 0; k < F::N; k++) out.v[k] = 0;
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    const int bit = 30 * i, k = bit >> 5, sh = bit & 31;
+    uint32_t l = (uint32_t)d[i];
+    if (k < F::N) out.v[k] |= l << sh;
+    if (sh > 2 && k + 1 < F::N) out.v[k + 1] |= l >> (32 - sh);
+  }
+  return out;
+}
+
+template <class F>
+MSM_HD Fe<F> fe_inv(const Fe<F>& a) {
+  Fe<F> r3;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r3.v[i] = F::R3(i);
+  return fe_mul(fe_inv_plain(a), r3);  // (x R)^-1 * R^3 / R = x^-1 R
 }
 
 // x -> x*R (to Montgomery) and back

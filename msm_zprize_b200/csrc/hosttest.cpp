@@ -30,6 +30,8 @@ static int fe_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 5: r = fe_from_mont(x); break;
     case 6: r = fe_sqr(x); break;
     case 7: r = fe_neg(x); break;
+    case 8: r = fe_inv_fermat(x); break;
+    case 9: r = fe_inv_plain(x); break;
     default: return -1;
   }
   st(out, r);

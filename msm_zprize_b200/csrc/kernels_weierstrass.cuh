@@ -169,7 +169,7 @@ __global__ void k_hist_scatter(SortArgs a) {
 
 // Block r computes, for tree round r, the exclusive scan over buckets of
 // pairs_r[b] = ceil(n_r[b] / 2), n_r[b] = ceil(cnt[b] / 2^r); block 0 also the max count.
-// po[r * NB + b], totals[r], totals[MAX_ROUNDS+1] = max count.
+// po[r * NB + b], totals[r], totals[MAX_ROUNDS+1] = max count, totals[MAX_ROUNDS+2] = sum of counts.
 static __global__ void k_scan(const uint32_t* __restrict__ cnt, uint32_t NB, uint32_t* __restrict__ po,
                        unsigned long long* __restrict__ totals) {
   __shared__ unsigned long long sh[1024];
@@ -178,11 +178,12 @@ static __global__ void k_scan(const uint32_t* __restrict__ cnt, uint32_t NB, uin
   int t = threadIdx.x, T = blockDim.x;
   uint32_t per = (NB + T - 1) / T;
   uint32_t b0 = min(NB, (uint32_t)t * per), b1 = min(NB, b0 + per);
-  unsigned long long sum = 0;
+  unsigned long long sum = 0, nent = 0;
   uint32_t mx = 0;
   for (uint32_t b = b0; b < b1; b++) {
     uint32_t c0 = cnt[b];
     mx = max(mx, c0);
+    nent += c0;
     uint32_t n = (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r);
     sum += (n + 1) >> 1;
   }
@@ -209,6 +210,7 @@ static __global__ void k_scan(const uint32_t* __restrict__ cnt, uint32_t NB, uin
     totals[r] = sh[t];
     if (r == 0) totals[MAX_ROUNDS + 1] = shmax[t];
   }
+  if (r == 0) atomicAdd(&totals[MAX_ROUNDS + 2], nent);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,87 @@
+"""Device input generators (replacing randomPointsFast / randomScalars, src/curve-random.ts) and
+size-independent properties at sizes the python oracle cannot reach."""
+import numpy as np
+import pytest
+
+from oracle import bigint_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mz():
+    import msm_zprize_b200 as m
+    return m
+
+
+def _gen(eng, mz, n, seed):
+    pb = eng.point_bytes(mz.LAYOUT_LE_BYTES)
+    d_pts = eng.dev_alloc(n * pb)
+    d_sc = eng.dev_alloc(n * 32)
+    eng.random_points_device(d_pts, n, seed)
+    eng.random_scalars_device(d_sc, n, seed + 1)
+    pts = eng.d2h(d_pts, n * pb).tobytes()
+    sc = eng.d2h(d_sc, n * 32).tobytes()
+    return d_pts, d_sc, pts, sc
+
+
+@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)])
+def test_generated_weierstrass_inputs(mz, name, params):
+    # src/curve-projective.test.ts / curve-twisted-edwards.test.ts:162-198: on curve, in subgroup
+    aff = O.WeierstrassAffine(params)
+    n, nb = 200, (48 if name == "bls12-377" else 32)
+    with mz.MsmEngine(name) as eng:
+        d_pts, d_sc, pts, sc = _gen(eng, mz, n, 11)
+        P = [(int.from_bytes(pts[i * 2 * nb:i * 2 * nb + nb], "little"),
+              int.from_bytes(pts[i * 2 * nb + nb:(i + 1) * 2 * nb], "little")) for i in range(n)]
+        S = [int.from_bytes(sc[i * 32:(i + 1) * 32], "little") for i in range(n)]
+        assert all(aff.is_on_curve(p) for p in P)
+        assert all(aff.is_in_subgroup(p) for p in P[:4])
+        assert len(set(P)) == n
+        assert all(s < params.q for s in S) and len(set(S)) == n
+        eng.set_bases_device(d_pts, n)
+        res = eng.run(d_sc, n, on_device=True)
+        assert (res.x, res.y) == O.msm(aff, S, P)
+
+
+def test_generated_te_inputs(mz):
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    n = 200
+    with mz.MsmEngine("ed-on-bls12-377") as eng:
+        d_pts, d_sc, pts, sc = _gen(eng, mz, n, 13)
+        P = [(int.from_bytes(pts[i * 64:i * 64 + 32], "little"), int.from_bytes(pts[i * 64 + 32:(i + 1) * 64], "little"))
+             for i in range(n)]
+        S = [int.from_bytes(sc[i * 32:(i + 1) * 32], "little") for i in range(n)]
+        assert all(te.is_on_curve(te.from_affine(p)) for p in P)
+        assert te.is_zero(te.scale(te.q, te.from_affine(P[0])))
+        assert all(s < te.q for s in S)
+        eng.set_bases_device(d_pts, n)
+        res = eng.run(d_sc, n, on_device=True)
+        assert (res.x, res.y) == te.to_affine(O.msm(te, S, [te.from_affine(p) for p in P]))
+
+
+@pytest.mark.parametrize("name,lg", [("bls12-377", 16), ("pallas", 16), ("ed-on-bls12-377", 16)])
+def test_large_n_properties(mz, name, lg):
+    """n = 2^16: (i) the result does not depend on the window size, (ii) linearity:
+    MSM(s, G) == MSM(s[:h], G[:h]) + MSM(s[h:], G[h:]) via run_partial + combine (the multi-GPU path),
+    (iii) Weierstrass: the batched-affine and the projective bucket method agree."""
+    n = 1 << lg
+    with mz.MsmEngine(name) as eng:
+        pb = eng.point_bytes(mz.LAYOUT_LE_BYTES)
+        d_pts, d_sc, _, _ = _gen(eng, mz, n, 21)
+        eng.set_bases_device(d_pts, n)
+        a = eng.run(d_sc, n, on_device=True)
+        b = eng.run(d_sc, n, on_device=True, window_bits=9)
+        assert (a.x, a.y, a.is_zero) == (b.x, b.y, b.is_zero)
+        if name != "ed-on-bls12-377":
+            p = eng.run(d_sc, n, on_device=True, form=mz.FORM_PROJECTIVE)
+            assert (a.x, a.y) == (p.x, p.y)
+        # two halves, combined like two GPUs would
+        h = n // 2 + 123
+        pbytes = eng.partial_bytes()
+        d_part = eng.dev_alloc(2 * pbytes)
+        eng.run_partial(d_sc, h, d_part, on_device=True)
+        eng.set_bases_device(d_pts + h * pb, n - h)
+        eng.run_partial(d_sc + h * 32, n - h, d_part + pbytes, on_device=True)
+        c = eng.combine(d_part, 2)
+        assert (a.x, a.y, a.is_zero) == (c.x, c.y, c.is_zero)

@@ -77,9 +77,12 @@ def test_field_ops(lib, field):
         assert fe_op(lib, field, 7, a) == (-a) % p
         assert fe_op(lib, field, 4, a) == a * R % p
         assert fe_op(lib, field, 5, a) == a * Ri % p
-    for a in vals[1:20]:
-        # Montgomery-domain inverse: (xR)^-1 * R^2
+    for a in vals[1:] + [rng.randrange(1, p) for _ in range(500)]:
+        # Montgomery-domain inverse: (xR)^-1 * R^2  (safegcd), plain inverse, and the Fermat cross-check
         assert fe_op(lib, field, 3, a) == pow(a, -1, p) * R * R % p
+        assert fe_op(lib, field, 9, a) == pow(a, -1, p)
+    for a in vals[1:12]:
+        assert fe_op(lib, field, 8, a) == pow(a, -1, p) * R * R % p
 
 
 @pytest.mark.parametrize("field,params,b3", [(0, O.BLS12_377, 3), (1, O.PALLAS, 15)])

@@ -69,6 +69,7 @@ def field_struct(name, p, n32, extra=None, w29_extra_bits=2):
     s += arr("P", limbs(p, n32))
     s += arr("ONE", limbs(R % p, n32))
     s += arr("R2", limbs(R * R % p, n32))
+    s += arr("R3", limbs(R * R * R % p, n32))
     s += arr("PM2", limbs(p - 2, n32))
     # limb29 Montgomery (R29 = 2^(29 n29)) <-> limb32 Montgomery conversion multipliers
     s += arr("FROM29", limbs(pow(2, 2 * rbits - 29 * n29, p), n32))
