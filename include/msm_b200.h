@@ -77,7 +77,7 @@ typedef struct msm_b200_timing {
   int window_bits;          /* c actually used */
   int n_windows;            /* K */
   int rounds;               /* batched-affine tree rounds */
-  unsigned long long n_adds;/* point additions performed in the accumulation */
+  unsigned long long n_adds;/* point additions finished inside the dominant kernel's launches */
 } msm_b200_timing;
 
 /* Result point, canonical affine (the normalisation that defines parity: Projective.toAffine +

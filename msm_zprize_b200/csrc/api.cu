@@ -136,7 +136,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
     }
     ctx->own_stream = true;
   }
-  cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, (MAX_ROUNDS + 3) * 8);
+  cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, N_TOTALS * 8);
   cudaError_t e2 = cudaMallocHost((void**)&ctx->h_result, 64 * 4);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     delete ctx;
@@ -152,7 +152,7 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* all[] = {&ctx->bases, &ctx->raw_points, &ctx->raw_scalars, &ctx->hs, &ctx->cnt, &ctx->cursor, &ctx->po,
                    &ctx->totals, &ctx->ent, &ctx->pairkey[0], &ctx->pairkey[1], &ctx->elem[0], &ctx->elem[1],
-                   &ctx->prefix, &ctx->red[0], &ctx->red[1], &ctx->partial, &ctx->result, &ctx->buckets, &ctx->rp_tables};
+                   &ctx->prefix, &ctx->red[0], &ctx->red[1], &ctx->partial, &ctx->result, &ctx->buckets, &ctx->rp_tables, &ctx->fin};
   for (DevBuf* b : all) release(*b);
   for (int i = 0; i < 8; i++) {
     release(ctx->lvl_pre[i]);

@@ -35,7 +35,7 @@ struct msm_b200_ctx {
   size_t n_bases = 0;
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
-  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables;
+  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin;
   unsigned long long* h_totals = nullptr;  // pinned
   uint32_t* h_result = nullptr;            // pinned
   std::vector<cudaEvent_t> ev;
@@ -179,25 +179,33 @@ template <class F>
 static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
   constexpr size_t FE = F::N * 4;
   size_t M[8];
-  int nl = 0;
+  int ns = 0;  // serial levels
   M[0] = M1;
-  // lvl_tot[l] = values of level l+1 (M[l] elements); lvl_pre[l] = their prefixes, then inverses
-  while (M[nl] > (size_t)TOP_MAX && nl < 6) {
-    size_t blocks = cdiv(M[nl], (size_t)UP_THREADS * UP_B1);
-    M[nl + 1] = blocks * UP_THREADS;
-    nl++;
+  // lvl_tot[l] = values of level l (M[l] elements); lvl_pre[l] = their prefixes / "others", then inverses
+  while (M[ns] > (size_t)TREE_MAX && ns < 5) {
+    size_t blocks = cdiv(M[ns], (size_t)UP_THREADS * UP_B1);
+    M[ns + 1] = blocks * UP_THREADS;
+    ns++;
   }
-  for (int l = 0; l <= nl; l++) RET_IF(ensure(ctx, ctx->lvl_pre[l], M[l] * FE));
-  for (int l = 1; l <= nl; l++) RET_IF(ensure(ctx, ctx->lvl_tot[l], M[l] * FE));
-  for (int l = 0; l < nl; l++) {
+  const bool two = M[ns] > (size_t)TREE_CTA;  // scan level below the top block?
+  const int top = ns + (two ? 1 : 0);
+  if (two) M[top] = cdiv(M[ns], TREE_CTA);
+  for (int l = 0; l <= top; l++) RET_IF(ensure(ctx, ctx->lvl_pre[l], (M[l] + 1) * FE));
+  for (int l = 1; l <= top; l++) RET_IF(ensure(ctx, ctx->lvl_tot[l], (M[l] + 1) * FE));
+  for (int l = 0; l < ns; l++)
     LAUNCH(ctx, k_up_fwd<F>, cdiv(M[l], (size_t)UP_THREADS * UP_B1), UP_THREADS, (const uint4*)ctx->lvl_tot[l].p, M[l],
            (uint4*)ctx->lvl_pre[l].p, (uint4*)ctx->lvl_tot[l + 1].p, M[l + 1]);
-  }
-  LAUNCH(ctx, k_inv_top<F>, cdiv(M[nl], 32), 32, (const uint4*)ctx->lvl_tot[nl].p, M[nl], (uint4*)ctx->lvl_pre[nl].p);
-  for (int l = nl - 1; l >= 0; l--) {
+  if (two)
+    LAUNCH(ctx, (k_tree_up<F, false>), (unsigned)M[top], TREE_CTA, (const uint4*)ctx->lvl_tot[ns].p, M[ns],
+           (uint4*)ctx->lvl_pre[ns].p, (uint4*)ctx->lvl_tot[top].p, M[top]);
+  LAUNCH(ctx, (k_tree_up<F, true>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top], (uint4*)ctx->lvl_pre[top].p,
+         (uint4*)nullptr, (size_t)0);
+  if (two)
+    LAUNCH(ctx, k_tree_down<F>, (unsigned)M[top], TREE_CTA, (uint4*)ctx->lvl_pre[ns].p, M[ns],
+           (const uint4*)ctx->lvl_pre[top].p, M[top]);
+  for (int l = ns - 1; l >= 0; l--)
     LAUNCH(ctx, k_up_bwd<F>, cdiv(M[l], (size_t)UP_THREADS * UP_B1), UP_THREADS, (const uint4*)ctx->lvl_tot[l].p, M[l],
            (uint4*)ctx->lvl_pre[l].p, (const uint4*)ctx->lvl_pre[l + 1].p, M[l + 1]);
-  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -220,9 +228,9 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   remaining -= gb;
   int cur = 0;
   while (remaining > 0) {
-    gb = remaining < 3 ? remaining : 3;
+    gb = remaining < 5 ? remaining : 5;  // one item per lane, groups of 2^gb lanes
     size_t out_items = items >> gb;
-    LAUNCH(ctx, (k_reduce_up<C>), cdiv(out_items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
+    LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
            (uint4*)ctx->red[cur ^ 1].p);
     items = out_items;
     remaining -= gb;
@@ -253,7 +261,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
   RET_IF(ensure(ctx, ctx->po, NB * 4));
-  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 3) * 8));
+  RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
   LAUNCH(ctx, k_load_scalars<S>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
@@ -271,10 +279,10 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.digits = nullptr;
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
-  CK(cudaMemsetAsync(ctx->totals.p, 0, (MAX_ROUNDS + 3) * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
   LAUNCH(ctx, k_scan, 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
          (unsigned long long*)ctx->totals.p);
-  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t P0 = ctx->h_totals[0];
   RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
@@ -358,7 +366,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
   RET_IF(ensure(ctx, ctx->po, (size_t)(MAX_ROUNDS + 1) * NB * 4));
-  RET_IF(ensure(ctx, ctx->totals, (MAX_ROUNDS + 3) * 8));
+  RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
   LAUNCH(ctx, k_glv<G>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
@@ -377,10 +385,10 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
   int e1 = T.mark();
   // --- offsets for every round, one host sync
-  CK(cudaMemsetAsync(ctx->totals.p, 0, (MAX_ROUNDS + 3) * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
   LAUNCH(ctx, k_scan, MAX_ROUNDS + 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
          (unsigned long long*)ctx->totals.p);
-  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, (MAX_ROUNDS + 3) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const unsigned long long maxcnt = ctx->h_totals[MAX_ROUNDS + 1];
   int R = 1;
@@ -415,10 +423,13 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->elem[0], ElemBuf<F>::bytes(ctx->h_totals[1] + 1)));
   RET_IF(ensure(ctx, ctx->elem[1], ElemBuf<F>::bytes(ctx->h_totals[2] + 1)));
   RET_IF(ensure(ctx, ctx->prefix, (P0 + 1) * FE));
+  RET_IF(ensure(ctx, ctx->fin, FinBuf<F>::bytes(NB)));
   std::vector<std::pair<int, int>> hot;
+  int rounds_run = 0;
   for (int r = 0; r < R; r++) {
     const size_t P = ctx->h_totals[r];
     const size_t Pn = ctx->h_totals[r + 1];
+    if (P == 0) break;
     RoundArgs<F> a;
     a.r = r;
     a.P = P;
@@ -434,6 +445,19 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.in.cap = P;
     a.out.base = (uint4*)ctx->elem[r & 1].p;
     a.out.cap = Pn;
+    a.fin.base = (uint4*)ctx->fin.p;
+    a.fin.cap = NB;
+    a.prefix = nullptr;
+    a.tot = nullptr;
+    a.invtot = nullptr;
+    a.M1 = 0;
+    if (P <= (size_t)FINISH_MAX) {  // tail: one thread per unfinished bucket
+      if (r == 0)
+        LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB);
+      else
+        LAUNCH(ctx, (k_finish<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB);
+      break;
+    }
     unsigned grid = cdiv(P, (size_t)ACC_THREADS * ACC_B0);
     size_t M1 = (size_t)grid * ACC_THREADS;
     RET_IF(ensure(ctx, ctx->lvl_tot[0], M1 * FE));
@@ -454,17 +478,17 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
       LAUNCH(ctx, (k_bwd<F, false>), grid, ACC_THREADS, a);
     int h1 = T.mark();
     hot.push_back({h0, h1});
-    n_adds += (r == 0 ? ctx->h_totals[MAX_ROUNDS + 2] : ctx->h_totals[r - 1]) - P;  // elements - pairs
+    n_adds += ctx->h_totals[MAX_ROUNDS + 3 + r];  // additions finished by this k_bwd launch
+    rounds_run++;
   }
   CK(cudaGetLastError());
   int e3 = T.mark();
   // --- bucket reduction
   {
     AffineBucketLoader<F, B3> ld;
-    ld.last.base = (uint4*)ctx->elem[(R - 1) & 1].p;
-    ld.last.cap = ctx->h_totals[R];
+    ld.fin = (const uint4*)ctx->fin.p;
+    ld.cap = NB;
     ld.cnt = (const uint32_t*)ctx->cnt.p;
-    ld.po_last = (const uint32_t*)ctx->po.p + (size_t)R * NB;
     RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
   }
   int e4 = T.mark();
@@ -479,7 +503,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     tm->hot_kernel_launches = (int)hot.size();
     tm->window_bits = c;
     tm->n_windows = K;
-    tm->rounds = R;
+    tm->rounds = rounds_run;
     tm->n_adds = n_adds;
   }
   return 0;

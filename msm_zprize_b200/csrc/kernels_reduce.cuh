@@ -36,6 +36,16 @@ struct WeierCurve {
     P.Z = ld_aos<F>(p + 2 * F::N / 4);
     return P;
   }
+  __device__ static Acc shfl_down(const Acc& a, int d) {
+    Acc r;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+      r.X.v[i] = __shfl_down_sync(0xffffffffu, a.X.v[i], d);
+      r.Y.v[i] = __shfl_down_sync(0xffffffffu, a.Y.v[i], d);
+      r.Z.v[i] = __shfl_down_sync(0xffffffffu, a.Z.v[i], d);
+    }
+    return r;
+  }
   // acc +/- base point `idx` (src/curve-projective.ts addMixed / subMixed)
   __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
     const uint4* p = bases + (size_t)idx * BASE_STRIDE * (2 * F::N / 4);
@@ -84,6 +94,17 @@ struct TeCurve {
     P.T = ld_aos<F>(p + 3 * F::N / 4);
     return P;
   }
+  __device__ static Acc shfl_down(const Acc& a, int d) {
+    Acc r;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) {
+      r.X.v[i] = __shfl_down_sync(0xffffffffu, a.X.v[i], d);
+      r.Y.v[i] = __shfl_down_sync(0xffffffffu, a.Y.v[i], d);
+      r.Z.v[i] = __shfl_down_sync(0xffffffffu, a.Z.v[i], d);
+      r.T.v[i] = __shfl_down_sync(0xffffffffu, a.T.v[i], d);
+    }
+    return r;
+  }
   __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
     const uint4* p = bases + (size_t)idx * (3 * F::N / 4);
     Niels<F> Q;
@@ -108,15 +129,17 @@ struct TeCurve {
 };
 
 // ---- level-0 loaders ----------------------------------------------------------------------
-// affine bucket sums left by the last round of the batched-affine tree
+// affine bucket sums left in the `fin` array by the batched-affine tree
 template <class F, uint32_t B3>
 struct AffineBucketLoader {
-  ElemBuf<F> last;
+  const uint4* fin;  // x chunks, then y chunks, `cap` elements each
+  size_t cap;
   const uint32_t* cnt;
-  const uint32_t* po_last;
   __device__ __forceinline__ void add_bucket(Proj<F>& run, uint32_t b) const {
     if (cnt[b] == 0) return;
-    Aff<F> A = last.load(2 * (size_t)po_last[b]);
+    Aff<F> A;
+    A.x = ld_soa<F>(fin, cap, b);
+    A.y = ld_soa<F>(fin + (size_t)(F::N / 4) * cap, cap, b);
     if (!aff_is_inf(A)) run = proj_add_mixed<F, B3>(run, A);
   }
 };
@@ -171,6 +194,46 @@ __global__ void k_reduce_up(const uint4* __restrict__ in, uint32_t n_items, int 
   uint4* o = out + (size_t)u * item_u4<C>();
   C::st(o, run);
   C::st(o + item_u4<C>() / 2, C::add(tri, xs));
+}
+
+// Levels >= 1 with one item per lane: groups of g = 2^gb consecutive lanes (g <= 32).
+//   S_j = sum_{t >= j} R_t   (suffix scan over the group, gb shuffle steps)
+//   X'  = sum_j X_j + sum_{j >= 1} S_j   (one add + gb-step tree reduction),  R' = g * S_0
+// Serial depth gb + 1 + gb additions for gb bits of the window instead of 3 * 2^gb.
+template <class C>
+__global__ void __launch_bounds__(64) k_reduce_warp(const uint4* __restrict__ in, uint32_t n_items, int gb,
+                                                    uint4* __restrict__ out) {
+  typedef typename C::Acc Acc;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = 1 << gb;
+  const int j = (int)(i & (uint32_t)(g - 1));
+  const bool live = i < n_items;  // n_items is a multiple of g, so whole groups are live or dead
+  const uint4* p = in + (size_t)(live ? i : 0) * item_u4<C>();
+  Acc S = live ? C::ld(p) : C::zero();
+  Acc Y = live ? C::ld(p + item_u4<C>() / 2) : C::zero();
+#pragma unroll 1
+  for (int d = 1; d < g; d <<= 1) {
+    Acc t = C::shfl_down(S, d);
+    Acc n = C::add(S, t);
+    if (j + d < g) S = n;
+  }
+  {
+    Acc n = C::add(Y, S);
+    if (j >= 1) Y = n;
+  }
+#pragma unroll 1
+  for (int d = g >> 1; d >= 1; d >>= 1) {
+    Acc t = C::shfl_down(Y, d);
+    Acc n = C::add(Y, t);
+    if (j < d) Y = n;
+  }
+#pragma unroll 1
+  for (int d = 0; d < gb; d++) S = C::dbl(S);
+  if (live && j == 0) {
+    uint4* o = out + (size_t)(i >> gb) * item_u4<C>();
+    C::st(o, S);
+    C::st(o + item_u4<C>() / 2, Y);
+  }
 }
 
 template <class C>

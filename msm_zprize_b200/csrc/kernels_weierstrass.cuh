@@ -18,10 +18,14 @@ namespace msm {
 
 constexpr int ACC_THREADS = 256;  // block size of the level-0 kernels
 constexpr int ACC_B0 = 8;         // pairs per thread, level 0
-constexpr int UP_THREADS = 32;    // block size of the upper product-tree levels
-constexpr int UP_B1 = 32;         // elements per thread, upper levels
-constexpr int TOP_MAX = 2048;     // at most this many Fermat inversions per round
+constexpr int UP_THREADS = 64;    // block size of the serial product-tree levels
+constexpr int UP_B1 = 8;          // elements per thread, serial levels
+constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree levels (one block per SM:
+                                  // a modmul step costs 0.62 us x warps per sub-partition)
+constexpr int TREE_MAX = 65536;   // serial levels until at most this many elements remain
 constexpr int MAX_ROUNDS = 30;
+constexpr int N_TOTALS = 2 * MAX_ROUNDS + 8;  // see k_scan
+constexpr int FINISH_MAX = 16384;  // finish the tree per bucket once at most this many pair slots are left
 
 // ------------------------------------------------------------------------------------------
 // ingest
@@ -167,55 +171,95 @@ __global__ void k_hist_scatter(SortArgs a) {
   }
 }
 
-// Block r computes, for tree round r, the exclusive scan over buckets of
-// pairs_r[b] = ceil(n_r[b] / 2), n_r[b] = ceil(cnt[b] / 2^r); block 0 also the max count.
-// po[r * NB + b], totals[r], totals[MAX_ROUNDS+1] = max count, totals[MAX_ROUNDS+2] = sum of counts.
-static __global__ void k_scan(const uint32_t* __restrict__ cnt, uint32_t NB, uint32_t* __restrict__ po,
-                       unsigned long long* __restrict__ totals) {
-  __shared__ unsigned long long sh[1024];
-  __shared__ uint32_t shmax[1024];
-  int r = blockIdx.x;
-  int t = threadIdx.x, T = blockDim.x;
-  uint32_t per = (NB + T - 1) / T;
-  uint32_t b0 = min(NB, (uint32_t)t * per), b1 = min(NB, b0 + per);
-  unsigned long long sum = 0, nent = 0;
+// Block r computes, for tree round r, the exclusive scan over buckets of the pair slots
+// pairs_r[b] = ceil(n_r[b] / 2) with n_r[b] = ceil(cnt[b] / 2^r) elements left -- but 0 once a bucket
+// is down to one element (r >= 1): its sum then already sits in the `fin` array and it leaves the
+// tree.  Block 0 also computes the max count.
+// po[r * NB + b], totals[r], totals[MAX_ROUNDS+1] = max count, totals[MAX_ROUNDS+2] = sum of counts,
+// totals[MAX_ROUNDS+3+r] = additions performed in round r (sum of floor(n_r / 2) over live buckets).
+// Tiled: 1024 threads x 4 consecutive buckets per tile, warp-shuffle block scan, running offset.
+static __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ cnt, uint32_t NB,
+                                                     uint32_t* __restrict__ po, unsigned long long* __restrict__ totals) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t tile_total;
+  const int r = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  unsigned long long running = 0, nent = 0, nadd = 0;
   uint32_t mx = 0;
-  for (uint32_t b = b0; b < b1; b++) {
-    uint32_t c0 = cnt[b];
-    mx = max(mx, c0);
-    nent += c0;
-    uint32_t n = (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r);
-    sum += (n + 1) >> 1;
-  }
-  sh[t] = sum;
-  shmax[t] = mx;
-  __syncthreads();
-  // inclusive Hillis-Steele scan over T partial sums
-  for (int off = 1; off < T; off <<= 1) {
-    unsigned long long v = (t >= off) ? sh[t - off] : 0;
-    uint32_t m = (t >= off) ? shmax[t - off] : 0;
+  const unsigned long long rnd = (1ull << r) - 1;
+  for (uint32_t base = 0; base < NB; base += 4096) {
+    uint32_t b0 = base + 4 * t;
+    uint32_t v[4];
+    uint32_t local = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t c0 = (b0 + j < NB) ? cnt[b0 + j] : 0u;
+      mx = max(mx, c0);
+      nent += c0;
+      uint32_t n = (uint32_t)(((unsigned long long)c0 + rnd) >> r);
+      v[j] = (n >= (r == 0 ? 1u : 2u)) ? ((n + 1) >> 1) : 0u;  // a bucket with one element left is done
+      nadd += n >> 1;
+      local += v[j];
+    }
+    // inclusive warp scan of `local`
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    sh[t] += v;
-    shmax[t] = max(shmax[t], m);
+    if (w == 0) {
+      uint32_t x = wsum[lane], xi = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
+        if (lane >= d) xi += o;
+      }
+      wsum[lane] = xi - x;  // exclusive prefix of the warp sums
+      if (lane == 31) tile_total = xi;
+    }
+    __syncthreads();
+    unsigned long long off = running + wsum[w] + (incl - local);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (b0 + j < NB) po[(size_t)r * NB + b0 + j] = (uint32_t)off;
+      off += v[j];
+    }
+    running += tile_total;
     __syncthreads();
   }
-  unsigned long long run = sh[t] - sum;
-  for (uint32_t b = b0; b < b1; b++) {
-    uint32_t c0 = cnt[b];
-    uint32_t n = (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r);
-    po[(size_t)r * NB + b] = (uint32_t)run;
-    run += (n + 1) >> 1;
+  if (t == 0) totals[r] = running;
+  atomicAdd(&totals[MAX_ROUNDS + 3 + r], nadd);
+  if (r == 0) {
+    atomicMax(&totals[MAX_ROUNDS + 1], (unsigned long long)mx);
+    atomicAdd(&totals[MAX_ROUNDS + 2], nent);
   }
-  if (t == T - 1) {
-    totals[r] = sh[t];
-    if (r == 0) totals[MAX_ROUNDS + 1] = shmax[t];
-  }
-  if (r == 0) atomicAdd(&totals[MAX_ROUNDS + 2], nent);
 }
 
 // ------------------------------------------------------------------------------------------
 // one round of the pairwise tree
 // ------------------------------------------------------------------------------------------
+// final bucket sums (affine, infinity-marked when the bucket cancelled out), indexed by bucket
+template <class F>
+struct FinBuf {
+  uint4* base;
+  size_t cap;
+  static constexpr int CH = F::N / 4;
+  __device__ __forceinline__ void store(size_t b, const Aff<F>& P) const {
+    st_soa<F>(base, cap, b, P.x);
+    st_soa<F>(base + (size_t)CH * cap, cap, b, P.y);
+  }
+  __device__ __forceinline__ Aff<F> load(size_t b) const {
+    Aff<F> P;
+    P.x = ld_soa<F>(base, cap, b);
+    P.y = ld_soa<F>(base + (size_t)CH * cap, cap, b);
+    return P;
+  }
+  static size_t bytes(size_t cap) { return (size_t)2 * CH * cap * sizeof(uint4); }
+};
+
 template <class F>
 struct RoundArgs {
   int r;                 // round number
@@ -230,6 +274,7 @@ struct RoundArgs {
   const uint4* bases;    // round 0: base points
   ElemBuf<F> in;         // round >= 1
   ElemBuf<F> out;
+  FinBuf<F> fin;         // buckets that are down to one element
   // batch inversion, level 0
   uint4* prefix;         // P elements, stride = P
   uint4* tot;            // one per thread, stride = M1
@@ -254,6 +299,39 @@ __device__ __forceinline__ void load_pair(const RoundArgs<F>& a, size_t i, Aff<F
   }
 }
 
+// Denominator of pair i for the forward pass.  Only the x coordinates are needed unless they are
+// equal (doubling / inverse pair), so the common path reads 2 x 48 bytes instead of 2 x 96: the
+// forward pass is HBM-bound (1 modmul per ~150 bytes), the backward pass is not.
+template <class F, bool R0>
+__device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i, Fe<F>& d) {
+  uint32_t b = a.pairkey[i];
+  uint32_t j = (uint32_t)i - a.po_r[b];
+  uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
+  if (!(2 * j + 1 < n)) return false;  // single element: passes through
+  Fe<F> xa, xb;
+  const uint4 *pa = nullptr, *pb = nullptr;
+  if (R0) {
+    uint2 e = reinterpret_cast<const uint2*>(a.ent)[i];
+    pa = a.bases + (size_t)ent_index(e.x) * (2 * F::N / 4);
+    pb = a.bases + (size_t)ent_index(e.y) * (2 * F::N / 4);
+    xa = ld_aos<F>(pa);
+    xb = ld_aos<F>(pb);
+    if (xa.v[F::N - 1] == AFF_INF_MARK || xb.v[F::N - 1] == AFF_INF_MARK) return false;
+    d = fe_sub(xb, xa);
+    if (!fe_is_zero(d)) return true;
+    Aff<F> A = gather_base<F>(a.bases, e.x), B = gather_base<F>(a.bases, e.y);
+    return aff_add_prepare(A, B, d) <= AFF_DBL;
+  } else {
+    xa = ld_soa<F>(a.in.coord(0, 0), a.in.cap, i);
+    xb = ld_soa<F>(a.in.coord(1, 0), a.in.cap, i);
+    if (xa.v[F::N - 1] == AFF_INF_MARK || xb.v[F::N - 1] == AFF_INF_MARK) return false;
+    d = fe_sub(xb, xa);
+    if (!fe_is_zero(d)) return true;
+    Aff<F> A = a.in.load(2 * i), B = a.in.load(2 * i + 1);
+    return aff_add_prepare(A, B, d) <= AFF_DBL;
+  }
+}
+
 // forward pass: exclusive prefix products of the denominators, per thread
 template <class F, bool R0>
 __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
@@ -264,12 +342,8 @@ __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
   for (int s = 0; s < ACC_B0; s++) {
     size_t i = chunk0 + (size_t)s * ACC_THREADS + threadIdx.x;
     if (i >= a.P) break;
-    Aff<F> A, B;
-    uint32_t b, j;
-    load_pair<F, R0>(a, i, A, B, b, j);
     Fe<F> d;
-    int cs = aff_add_prepare(A, B, d);
-    if (cs <= AFF_DBL) {
+    if (fwd_denominator<F, R0>(a, i, d)) {
       st_soa<F>(a.prefix, a.P, i, run);
       run = fe_mul(run, d);
     }
@@ -299,10 +373,38 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
       inv = fe_mul(inv, d);
     }
     Aff<F> R = aff_add_finish(cs, A, B, id);
-    size_t e = 2 * (size_t)a.po_n[b] + j;
-    a.out.store(e, R);
-    if (!(e & 1)) a.pairkey_next[e >> 1] = b;
+    uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
+    if (n <= 2) {  // one element left after this round: the bucket sum
+      a.fin.store(b, R);
+    } else {
+      size_t e = 2 * (size_t)a.po_n[b] + j;
+      a.out.store(e, R);
+      if (!(e & 1)) a.pairkey_next[e >> 1] = b;
+    }
   }
+}
+
+// Tail of the tree: when few pair slots are left, every unfinished bucket is summed by one thread
+// (projective mixed additions + its own inversion) instead of running more latency-bound rounds.
+template <class F, uint32_t B3, bool R0>
+__global__ void __launch_bounds__(64) k_finish(RoundArgs<F> a, uint32_t NB) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
+  if (n < (R0 ? 1u : 2u)) return;
+  size_t e0 = 2 * (size_t)a.po_r[b];
+  Aff<F> A = R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0);
+  if (n == 1) {
+    a.fin.store(b, A);
+    return;
+  }
+  Proj<F> acc = proj_from_aff(A);
+#pragma unroll 1
+  for (uint32_t j = 1; j < n; j++) {
+    Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
+    if (!aff_is_inf(Q)) acc = proj_add_mixed<F, B3>(acc, Q);
+  }
+  a.fin.store(b, proj_to_aff(acc));
 }
 
 // upper levels of the product tree: plain arrays of field elements
@@ -341,11 +443,103 @@ __global__ void __launch_bounds__(UP_THREADS) k_up_bwd(const uint4* __restrict__
   }
 }
 
+// ---- scan-based top of the product tree (latency: ~25 dependent modmuls for a 1024x reduction
+// instead of 3 per element in a serial chain) ------------------------------------------------
 template <class F>
-__global__ void k_inv_top(const uint4* __restrict__ val, size_t M, uint4* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ Fe<F> fe_shfl_up(const Fe<F>& v, int d) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_up_sync(0xffffffffu, v.v[i], d);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_shfl_down(const Fe<F>& v, int d) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_shfl(const Fe<F>& v, int src) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void fe_to_smem(uint32_t* s, const Fe<F>& v) {
+#pragma unroll
+  for (int i = 0; i < F::N; i++) s[i] = v.v[i];
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_from_smem(const uint32_t* s) {
+  Fe<F> v;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) v.v[i] = s[i];
+  return v;
+}
+
+// inclusive prefix (p) and suffix (s) products across the lanes of a warp
+template <class F>
+__device__ __forceinline__ void warp_scan_products(const Fe<F>& v, int lane, Fe<F>& p, Fe<F>& s) {
+  p = v;
+  s = v;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Fe<F> tp = fe_shfl_up(p, d), ts = fe_shfl_down(s, d);
+    Fe<F> np = fe_mul(p, tp), ns = fe_mul(s, ts);
+    p = fe_select(lane >= d, np, p);
+    s = fe_select(lane + d < 32, ns, s);
+  }
+}
+
+// One block handles TREE_CTA elements: `others[i]` = product of all the block's elements but i,
+// `tot[block]` = product of all of them.  TOP: the block is the whole level; it inverts its total
+// and writes the individual inverses straight to `others`.
+template <class F, bool TOP>
+__global__ void __launch_bounds__(TREE_CTA) k_tree_up(const uint4* __restrict__ val, size_t M, uint4* __restrict__ others,
+                                                      uint4* __restrict__ tot, size_t Mn) {
+  constexpr int NW = TREE_CTA / 32;
+  __shared__ uint32_t wtot[32 * F::N], wpre[32 * F::N], wsuf[32 * F::N], binv[F::N];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const size_t i = (size_t)blockIdx.x * TREE_CTA + t;
+  Fe<F> v = (i < M) ? ld_soa<F>(val, M, i) : fe_one<F>();
+  Fe<F> p, s;
+  warp_scan_products(v, lane, p, s);
+  if (lane == 31) fe_to_smem<F>(wtot + w * F::N, p);
+  __syncthreads();
+  if (w == 0) {
+    Fe<F> x = (lane < NW) ? fe_from_smem<F>(wtot + lane * F::N) : fe_one<F>(), xp, xs;
+    warp_scan_products(x, lane, xp, xs);
+    Fe<F> pre = fe_shfl_up(xp, 1), suf = fe_shfl_down(xs, 1);
+    if (lane == 0) pre = fe_one<F>();
+    if (lane == 31) suf = fe_one<F>();
+    fe_to_smem<F>(wpre + lane * F::N, pre);
+    fe_to_smem<F>(wsuf + lane * F::N, suf);
+    if (lane == 31) {
+      if (TOP)
+        fe_to_smem<F>(binv, fe_inv(xp));
+      else
+        st_soa<F>(tot, Mn, blockIdx.x, xp);
+    }
+  }
+  __syncthreads();
+  Fe<F> pe = fe_shfl_up(p, 1), se = fe_shfl_down(s, 1);
+  if (lane == 0) pe = fe_one<F>();
+  if (lane == 31) se = fe_one<F>();
+  Fe<F> o = fe_mul(fe_mul(fe_from_smem<F>(wpre + w * F::N), pe), fe_mul(se, fe_from_smem<F>(wsuf + w * F::N)));
+  if (TOP) o = fe_mul(o, fe_from_smem<F>(binv));
+  if (i < M) st_soa<F>(others, M, i, o);
+}
+
+// others[i] <- invtot[block] * others[i]  = 1 / val[i]
+template <class F>
+__global__ void __launch_bounds__(TREE_CTA) k_tree_down(uint4* __restrict__ others, size_t M, const uint4* __restrict__ invtot,
+                                                        size_t Mn) {
+  const size_t i = (size_t)blockIdx.x * TREE_CTA + threadIdx.x;
   if (i >= M) return;
-  st_soa<F>(out, M, i, fe_inv(ld_soa<F>(val, M, i)));
+  Fe<F> it = ld_soa<F>(invtot, Mn, blockIdx.x);
+  st_soa<F>(others, M, i, fe_mul(it, ld_soa<F>(others, M, i)));
 }
 
 }  // namespace msm
