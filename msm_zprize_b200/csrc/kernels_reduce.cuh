@@ -13,6 +13,34 @@
 
 namespace msm {
 
+// ------------------------------------------------------------------------------------------
+// Quad-cooperative point operations for the latency-bound tail (Horner over the windows):
+// four adjacent lanes hold identical copies of the point and each computes ONE of up to four
+// independent field products of a formula layer, then all four exchange the results by shuffle.
+// A doubling is 2 product layers instead of 8 sequential modmuls (one lone warp needs 0.62 us
+// per modmul because the IMAD.WIDE pipe accepts one warp instruction per 4 cycles).
+// ------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void quad_mul4(const Fe<F>& a0, const Fe<F>& b0, const Fe<F>& a1, const Fe<F>& b1,
+                                          const Fe<F>& a2, const Fe<F>& b2, const Fe<F>& a3, const Fe<F>& b3,
+                                          Fe<F>& p0, Fe<F>& p1, Fe<F>& p2, Fe<F>& p3) {
+  const int lane = threadIdx.x & 31, q = lane & 3, base = lane & ~3;
+  Fe<F> x, y;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) {
+    x.v[i] = q == 0 ? a0.v[i] : (q == 1 ? a1.v[i] : (q == 2 ? a2.v[i] : a3.v[i]));
+    y.v[i] = q == 0 ? b0.v[i] : (q == 1 ? b1.v[i] : (q == 2 ? b2.v[i] : b3.v[i]));
+  }
+  Fe<F> p = fe_mul(x, y);
+#pragma unroll
+  for (int i = 0; i < F::N; i++) {
+    p0.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 0);
+    p1.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 1);
+    p2.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 2);
+    p3.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 3);
+  }
+}
+
 // ---- curve-form traits ------------------------------------------------------------------
 template <class F_, uint32_t B3_>
 struct WeierCurve {
@@ -55,6 +83,45 @@ struct WeierCurve {
     if (aff_is_inf(Q)) return a;
     if (neg) Q.y = fe_neg(Q.y);
     return proj_add_mixed<F, B3_>(a, Q);
+  }
+  // quad-cooperative doubling / addition (same formulas as proj_dbl / proj_add, RCB16 alg. 9 / 7)
+  __device__ static Acc dbl_quad(const Acc& P) {
+    Fe<F> t0, t1, t2, xy;
+    quad_mul4<F>(P.Y, P.Y, P.Y, P.Z, P.Z, P.Z, P.X, P.Y, t0, t1, t2, xy);
+    Fe<F> z3 = fe_dbl(fe_dbl(fe_dbl(t0)));
+    t2 = fe_mul_small(t2, B3_);
+    Fe<F> y3 = fe_add(t0, t2);
+    Fe<F> t23 = fe_add(fe_dbl(t2), t2);
+    Fe<F> t0b = fe_sub(t0, t23);
+    Fe<F> x3, zz, yy, xx;
+    quad_mul4<F>(t2, z3, t1, z3, t0b, y3, t0b, xy, x3, zz, yy, xx);
+    Acc R;
+    R.X = fe_dbl(xx);
+    R.Y = fe_add(x3, yy);
+    R.Z = zz;
+    return R;
+  }
+  __device__ static Acc add_quad(const Acc& P, const Acc& Q) {
+    Fe<F> t0, t1, t2, t3, t4, y3, d0, d1;
+    quad_mul4<F>(P.X, Q.X, P.Y, Q.Y, P.Z, Q.Z, fe_add(P.X, P.Y), fe_add(Q.X, Q.Y), t0, t1, t2, t3);
+    quad_mul4<F>(fe_add(P.Y, P.Z), fe_add(Q.Y, Q.Z), fe_add(P.X, P.Z), fe_add(Q.X, Q.Z), P.X, P.X, P.X, P.X, t4, y3,
+                 d0, d1);
+    t3 = fe_sub(t3, fe_add(t0, t1));
+    t4 = fe_sub(t4, fe_add(t1, t2));
+    y3 = fe_sub(y3, fe_add(t0, t2));
+    t0 = fe_add(fe_dbl(t0), t0);
+    t2 = fe_mul_small(t2, B3_);
+    Fe<F> z3 = fe_add(t1, t2);
+    t1 = fe_sub(t1, t2);
+    y3 = fe_mul_small(y3, B3_);
+    Fe<F> a, b, c, d, e, f;
+    quad_mul4<F>(t3, t1, t4, y3, t1, z3, y3, t0, a, b, c, d);
+    quad_mul4<F>(z3, t4, t0, t3, t0, t0, t0, t0, e, f, d0, d1);
+    Acc R;
+    R.X = fe_sub(a, b);
+    R.Y = fe_add(c, d);
+    R.Z = fe_add(e, f);
+    return R;
   }
   // canonical affine output words: x | y | is_zero
   __device__ static void normalise(const Acc& a, uint32_t* out) {
@@ -112,6 +179,31 @@ struct TeCurve {
     Q.ym = ld_aos<F>(p + F::N / 4);
     Q.kt = ld_aos<F>(p + 2 * F::N / 4);
     return ext_add_niels<F>(a, Q, neg);
+  }
+  // quad-cooperative doubling (dedicated a = -1 formula dbl-2008-hwcd: 4M + 4S in 2 layers; the
+  // reference doubles with the unified addition, src/curve-twisted-edwards.ts:215-227 -- same point)
+  __device__ static Acc dbl_quad(const Acc& P) {
+    Fe<F> A, B, ZZ, S;
+    quad_mul4<F>(P.X, P.X, P.Y, P.Y, P.Z, P.Z, fe_add(P.X, P.Y), fe_add(P.X, P.Y), A, B, ZZ, S);
+    Fe<F> Cc = fe_dbl(ZZ);
+    Fe<F> D = fe_neg(A);
+    Fe<F> E = fe_sub(fe_sub(S, A), B);
+    Fe<F> G = fe_add(D, B);
+    Fe<F> Fv = fe_sub(G, Cc);
+    Fe<F> H = fe_sub(D, B);
+    Acc R;
+    quad_mul4<F>(E, Fv, G, H, E, H, Fv, G, R.X, R.Y, R.T, R.Z);
+    return R;
+  }
+  __device__ static Acc add_quad(const Acc& P, const Acc& Q) {
+    Fe<F> A, B, TT, ZZ, Cc, d0, d1, d2;
+    quad_mul4<F>(fe_sub(P.Y, P.X), fe_sub(Q.Y, Q.X), fe_add(P.Y, P.X), fe_add(Q.Y, Q.X), P.T, Q.T, P.Z, Q.Z, A, B, TT, ZZ);
+    quad_mul4<F>(TT, fe_k2d<F>(), TT, TT, TT, TT, TT, TT, Cc, d0, d1, d2);
+    Fe<F> D = fe_dbl(ZZ);
+    Fe<F> E = fe_sub(B, A), Fv = fe_sub(D, Cc), G = fe_add(D, Cc), H = fe_add(B, A);
+    Acc R;
+    quad_mul4<F>(E, Fv, G, H, E, H, Fv, G, R.X, R.Y, R.T, R.Z);
+    return R;
   }
   // (X/Z, Y/Z): src/bigint/twisted-edwards.ts:39-45; is_zero flags the neutral point (0, 1)
   __device__ static void normalise(const Acc& a, uint32_t* out) {
@@ -236,17 +328,17 @@ __global__ void __launch_bounds__(64) k_reduce_warp(const uint4* __restrict__ in
   }
 }
 
+// One warp; every lane quad runs the same Horner chain cooperatively (src/msm-batched-affine.ts:310-321).
 template <class C>
-__global__ void k_horner(const uint4* __restrict__ items, int K, int c, uint4* __restrict__ partial) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_horner(const uint4* __restrict__ items, int K, int c, uint4* __restrict__ partial) {
   typename C::Acc acc = C::ld(items + (size_t)(K - 1) * item_u4<C>() + item_u4<C>() / 2);
 #pragma unroll 1
   for (int k = K - 2; k >= 0; k--) {
 #pragma unroll 1
-    for (int d = 0; d < c; d++) acc = C::dbl(acc);
-    acc = C::add(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
+    for (int d = 0; d < c; d++) acc = C::dbl_quad(acc);
+    acc = C::add_quad(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
   }
-  C::st(partial, acc);
+  if (threadIdx.x == 0) C::st(partial, acc);
 }
 
 template <class C>
