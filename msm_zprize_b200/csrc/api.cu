@@ -126,6 +126,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   ctx = new msm_b200_ctx();
   ctx->device = device;
   ctx->curve = curve;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {

@@ -30,6 +30,7 @@ struct msm_b200_ctx {
   bool own_stream = false;
   std::string err;
   int launches = 0;
+  int sm_count = 148;
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
@@ -451,6 +452,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.tot = nullptr;
     a.invtot = nullptr;
     a.M1 = 0;
+    a.B0 = 0;
     if (P <= (size_t)FINISH_MAX) {  // tail: one thread per unfinished bucket
       if (r == 0)
         LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB);
@@ -458,7 +460,20 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
         LAUNCH(ctx, (k_finish<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB);
       break;
     }
-    unsigned grid = cdiv(P, (size_t)ACC_THREADS * ACC_B0);
+    // pairs per thread: small rounds run as ONE full wave of resident blocks (no tail, few thread
+    // totals for the product tree); large rounds as ~ACC_WAVES waves so that dynamic block
+    // scheduling evens out the SMs
+    size_t per_wave = (size_t)ACC_RESIDENT * ctx->sm_count * ACC_THREADS;
+    int B0;
+    if (P <= (size_t)ACC_SINGLE_WAVE_MAX) {
+      B0 = (int)cdiv(P, per_wave);
+      if (B0 < ACC_MIN_PAIRS) B0 = ACC_MIN_PAIRS;
+    } else {
+      B0 = (int)cdiv(P, per_wave * ACC_WAVES);
+      if (B0 > ACC_MAX_PAIRS) B0 = ACC_MAX_PAIRS;
+    }
+    a.B0 = B0;
+    unsigned grid = cdiv(P, (size_t)ACC_THREADS * B0);
     size_t M1 = (size_t)grid * ACC_THREADS;
     RET_IF(ensure(ctx, ctx->lvl_tot[0], M1 * FE));
     RET_IF(ensure(ctx, ctx->lvl_pre[0], M1 * FE));

@@ -17,7 +17,11 @@
 namespace msm {
 
 constexpr int ACC_THREADS = 256;  // block size of the level-0 kernels
-constexpr int ACC_B0 = 8;         // pairs per thread, level 0
+constexpr int ACC_MIN_PAIRS = 2;  // pairs per thread are chosen per round (RoundArgs::B0) between these
+constexpr int ACC_MAX_PAIRS = 32; //   bounds so that the grid is about ACC_WAVES full waves of blocks
+constexpr int ACC_WAVES = 8;      //   (dynamic block scheduling balances the SMs; few waves leave a tail)
+constexpr int ACC_SINGLE_WAVE_MAX = 4 << 20;  // rounds with at most this many pairs run as one wave
+constexpr int ACC_RESIDENT = 2;   // resident blocks per SM of k_bwd (126 registers x 256 threads)
 constexpr int UP_THREADS = 64;    // block size of the serial product-tree levels
 constexpr int UP_B1 = 8;          // elements per thread, serial levels
 constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree levels (one block per SM:
@@ -280,6 +284,7 @@ struct RoundArgs {
   uint4* tot;            // one per thread, stride = M1
   const uint4* invtot;   // inverse of tot, same layout
   size_t M1;
+  int B0;                // pairs per thread: a block owns ACC_THREADS * B0 consecutive pairs
 };
 
 template <class F, bool R0>
@@ -332,15 +337,17 @@ __device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i,
   }
 }
 
-// forward pass: exclusive prefix products of the denominators, per thread
+// forward pass: exclusive prefix products of the denominators, per thread.
+// A block owns ACC_THREADS * B0 consecutive pairs; thread t takes pairs t, t + 256, ... of them, so
+// every warp access is coalesced.
 template <class F, bool R0>
 __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
-  size_t chunk0 = (size_t)blockIdx.x * (ACC_THREADS * ACC_B0);
-  size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
+  const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
+  const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
   Fe<F> run = fe_one<F>();
 #pragma unroll 1
-  for (int s = 0; s < ACC_B0; s++) {
-    size_t i = chunk0 + (size_t)s * ACC_THREADS + threadIdx.x;
+  for (int s = 0; s < a.B0; s++) {
+    const size_t i = chunk0 + (size_t)s * ACC_THREADS + threadIdx.x;
     if (i >= a.P) break;
     Fe<F> d;
     if (fwd_denominator<F, R0>(a, i, d)) {
@@ -354,12 +361,13 @@ __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
 // backward pass: individual inverses from the running inverse, then finish the additions
 template <class F, bool R0>
 __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
-  size_t chunk0 = (size_t)blockIdx.x * (ACC_THREADS * ACC_B0);
-  size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
+  const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
+  const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
   Fe<F> inv = ld_soa<F>(a.invtot, a.M1, gid);
+  // same pairs as the forward pass, in reverse order
 #pragma unroll 1
-  for (int s = ACC_B0 - 1; s >= 0; s--) {
-    size_t i = chunk0 + (size_t)s * ACC_THREADS + threadIdx.x;
+  for (int s = a.B0 - 1; s >= 0; s--) {
+    const size_t i = chunk0 + (size_t)s * ACC_THREADS + threadIdx.x;
     if (i >= a.P) continue;
     Aff<F> A, B;
     uint32_t b, j;
