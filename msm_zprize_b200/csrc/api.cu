@@ -16,8 +16,13 @@ static const CurveOps* ops_of(int curve) {
   return nullptr;
 }
 
-static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device) {
+static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device,
+                          bool overlapped = false) {
   if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
+  if (ctx->bases_pending) {  // a previous overlapped upload that was never consumed
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->bases_pending = false;
+  }
   if (layout != MSM_LAYOUT_LIMB29_MONT && layout != MSM_LAYOUT_LE_BYTES) return fail(ctx, MSM_E_INVALID, "bad point layout");
   if (n == 0 || !points) {
     ctx->n_bases = 0;
@@ -26,13 +31,27 @@ static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int l
   if (n > ((size_t)1 << 30)) return fail(ctx, MSM_E_INVALID, "too many points (max 2^30)");
   CK(cudaSetDevice(ctx->device));
   const void* d_in = points;
+  cudaStream_t main_stream = ctx->stream;
+  if (overlapped) {
+    // everything queued on the main stream so far (earlier calls reading the old bases) first
+    CK(cudaEventRecord(ctx->bases_ready, main_stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->bases_ready, 0));
+    ctx->stream = ctx->copy_stream;
+  }
+  int rc = 0;
   if (!on_device) {
     size_t bytes = n * point_bytes(ctx->curve, layout);
-    RET_IF(ensure(ctx, ctx->raw_points, bytes));
-    CK(cudaMemcpyAsync(ctx->raw_points.p, points, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ensure(ctx, ctx->raw_points, bytes);
+    if (rc == 0 && cudaMemcpyAsync(ctx->raw_points.p, points, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      rc = fail(ctx, MSM_E_CUDA, "H2D copy of the points failed");
     d_in = ctx->raw_points.p;
   }
-  RET_IF(ops_of(ctx->curve)->ingest(ctx, d_in, n, layout));
+  if (rc == 0) rc = ops_of(ctx->curve)->ingest(ctx, d_in, n, layout);
+  if (overlapped) {
+    if (rc == 0 && cudaEventRecord(ctx->bases_ready, ctx->copy_stream) == cudaSuccess) ctx->bases_pending = true;
+    ctx->stream = main_stream;
+  }
+  RET_IF(rc);
   ctx->n_bases = n;
   return 0;
 }
@@ -72,6 +91,7 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
   else
     rc = ops_of(ctx->curve)->run(ctx, d_s, n, layout, form, c, tm, digits_dump_dev);
   RET_IF(rc);
+  RET_IF(wait_for_bases(ctx));  // (no-op unless the MSM never touched the bases, e.g. all-zero scalars)
   if (tm) {
     tm->h2d_ms = T.ms(t0, t1);
     tm->kernel_launches = ctx->launches;
@@ -137,6 +157,11 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
     }
     ctx->own_stream = true;
   }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->bases_ready, cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, MSM_E_CUDA, "stream / event creation failed");
+  }
   cudaError_t e1 = cudaMallocHost((void**)&ctx->h_totals, N_TOTALS * 8);
   cudaError_t e2 = cudaMallocHost((void**)&ctx->h_result, 64 * 4);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -162,6 +187,8 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   for (auto e : ctx->ev) cudaEventDestroy(e);
   if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->bases_ready) cudaEventDestroy(ctx->bases_ready);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -219,7 +246,7 @@ int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, cons
   if (ctx) ctx->launches = 0;
   Timer T(ctx ? ctx : nullptr);
   int i0 = ctx ? T.mark() : 0;
-  RET_IF(set_bases_impl(ctx, points, n, point_layout, 0));
+  RET_IF(set_bases_impl(ctx, points, n, point_layout, 0, /*overlapped=*/true));
   int i1 = T.mark();
   int launches0 = ctx->launches;
   RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, timing));

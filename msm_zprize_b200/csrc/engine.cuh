@@ -28,6 +28,11 @@ struct msm_b200_ctx {
   int curve = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // one-shot call: points are copied and ingested on a second stream while the scalars are already
+  // being decomposed and sorted; the first kernel that reads the bases waits for this event
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t bases_ready = nullptr;
+  bool bases_pending = false;
   std::string err;
   int launches = 0;
   int sm_count = 148;
@@ -99,6 +104,15 @@ static void release(DevBuf& b) {
   } while (0)
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// call before the first kernel that reads ctx->bases
+static int wait_for_bases(msm_b200_ctx* ctx) {
+  if (ctx->bases_pending) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->bases_ready, 0));
+    ctx->bases_pending = false;
+  }
+  return 0;
+}
 
 static int ceil_log2_sz(size_t n) {
   int k = 0;
@@ -221,7 +235,7 @@ template <class C, class Loader>
 static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K, int c) {
   constexpr size_t ITEM = (size_t)item_u4<C>() * 16;
   int remaining = c - 1;
-  int gb = remaining < 3 ? remaining : 3;
+  int gb = remaining < 3 ? remaining : 3;  // level 0: 8 buckets per thread
   size_t items = NB >> gb;
   RET_IF(ensure(ctx, ctx->red[0], items * ITEM));
   RET_IF(ensure(ctx, ctx->red[1], (items / 2 + 1) * ITEM));
@@ -291,6 +305,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   LAUNCH(ctx, k_hist_scatter8<true>, cdiv(n, 256), 256, sa);
   int e2 = T.mark();
   RET_IF(ensure(ctx, ctx->buckets, NB * C::ACC_FE * FE));
+  RET_IF(wait_for_bases(ctx));
   int h0 = T.mark();
   LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
          (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);
@@ -427,6 +442,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->fin, FinBuf<F>::bytes(NB)));
   std::vector<std::pair<int, int>> hot;
   int rounds_run = 0;
+  RET_IF(wait_for_bases(ctx));
   for (int r = 0; r < R; r++) {
     const size_t P = ctx->h_totals[r];
     const size_t Pn = ctx->h_totals[r + 1];

@@ -250,10 +250,14 @@ __host__ __device__ constexpr int item_u4() {
   return 2 * C::ACC_FE * C::F::N / 4;
 }
 
+// Level 0: one thread per group of g = 2^gb consecutive buckets (weights j + 1):
+//   run = sum B_j,  tri = sum (j + 1) B_j   ->  item (R = g * run, X = tri).
+// (A lane-quad version of this level was measured slower: the level is throughput-bound, 2 complete
+// additions per bucket, and quads only help latency.)
 template <class C, class Loader>
-__global__ void k_reduce0(Loader ld, uint32_t NB, int gb, uint4* __restrict__ out) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t g = 1u << gb;
+__global__ void __launch_bounds__(64) k_reduce0(Loader ld, uint32_t NB, int gb, uint4* __restrict__ out) {
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = 1u << gb;
   if ((size_t)u * g >= NB) return;
   typename C::Acc run = C::zero(), tri = C::zero();
 #pragma unroll 1
@@ -266,26 +270,6 @@ __global__ void k_reduce0(Loader ld, uint32_t NB, int gb, uint4* __restrict__ ou
   uint4* o = out + (size_t)u * item_u4<C>();
   C::st(o, run);
   C::st(o + item_u4<C>() / 2, tri);
-}
-
-template <class C>
-__global__ void k_reduce_up(const uint4* __restrict__ in, uint32_t n_items, int gb, uint4* __restrict__ out) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t g = 1u << gb;
-  if ((size_t)u * g >= n_items) return;
-  typename C::Acc run = C::zero(), tri = C::zero(), xs = C::zero();
-#pragma unroll 1
-  for (int jj = (int)g - 1; jj >= 0; jj--) {
-    const uint4* p = in + (size_t)(u * g + jj) * item_u4<C>();
-    xs = C::add(xs, C::ld(p + item_u4<C>() / 2));
-    run = C::add(run, C::ld(p));
-    if (jj > 0) tri = C::add(tri, run);
-  }
-#pragma unroll 1
-  for (int d = 0; d < gb; d++) run = C::dbl(run);
-  uint4* o = out + (size_t)u * item_u4<C>();
-  C::st(o, run);
-  C::st(o + item_u4<C>() / 2, C::add(tri, xs));
 }
 
 // Levels >= 1 with one item per lane: groups of g = 2^gb consecutive lanes (g <= 32).
