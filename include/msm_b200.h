@@ -25,7 +25,8 @@ typedef struct msm_b200_ctx msm_b200_ctx;
 enum msm_b200_curve {
   MSM_CURVE_BLS12_377_G1 = 0, /* short Weierstrass a=0, GLV, 377-bit base field */
   MSM_CURVE_PALLAS = 1,       /* short Weierstrass a=0, GLV, 255-bit base field */
-  MSM_CURVE_ED_ON_BLS12_377 = 2 /* twisted Edwards a=-1, 253-bit base field */
+  MSM_CURVE_ED_ON_BLS12_377 = 2, /* twisted Edwards a=-1, 253-bit base field */
+  MSM_CURVE_BLS12_381_G1 = 3     /* short Weierstrass a=0, GLV, 381-bit base field (src/concrete/bls12-381.params.ts) */
 };
 
 /* algorithm ("form"): which of the reference's MSMs the call mirrors */
@@ -158,7 +159,7 @@ int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, 
 /* -- test / measurement hooks ----------------------------------------------------------------
  * Field ops on the device, element-wise over `n` elements (32-bit limbs, internal Montgomery
  * form) -- the device side of the reference's per-op tests (src/field.test.ts:15-155).
- * field: 0 BLS12-377 Fq, 1 Pallas Fp, 2 BLS12-377 Fr.  op: 0 mul, 1 add, 2 sub, 3 inverse. */
+ * field: 0 BLS12-377 Fq, 1 Pallas Fp, 2 BLS12-377 Fr, 3 BLS12-381 Fq.  op: 0 mul, 1 add, 2 sub, 3 inverse. */
 int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host,
                            const uint32_t* b_host, uint32_t* out_host, size_t n);
 /* GLV decomposition + signed digits on the device for `n` scalars (LE_BYTES): writes

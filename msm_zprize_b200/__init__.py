@@ -4,10 +4,10 @@ mitschabaude/msm-zprize (scripts/run-msm-377.ts, run-msm-pallas.ts, run-msm-ed-3
 The CUDA engine lives in csrc/ (libmsm_b200.so, C ABI in include/msm_b200.h); this package is
 the host-side mirror of the reference's `Parallel` interface (src/parallel.ts) over that ABI.
 """
-from ._lib import (CURVE_BLS12_377_G1, CURVE_ED_ON_BLS12_377, CURVE_PALLAS, FORM_AFFINE_GLV,
+from ._lib import (CURVE_BLS12_377_G1, CURVE_BLS12_381_G1, CURVE_ED_ON_BLS12_377, CURVE_PALLAS, FORM_AFFINE_GLV,
                    FORM_PROJECTIVE, FORM_TE_EXTENDED, LAYOUT_LE_BYTES, LAYOUT_LIMB29_MONT, MsmError)
 from .engine import MsmEngine, MsmResult, PinnedBuffer
 
 __all__ = ["MsmEngine", "MsmResult", "MsmError", "PinnedBuffer", "CURVE_BLS12_377_G1", "CURVE_PALLAS",
-           "CURVE_ED_ON_BLS12_377", "FORM_AFFINE_GLV", "FORM_PROJECTIVE", "FORM_TE_EXTENDED",
+           "CURVE_ED_ON_BLS12_377", "CURVE_BLS12_381_G1", "FORM_AFFINE_GLV", "FORM_PROJECTIVE", "FORM_TE_EXTENDED",
            "LAYOUT_LE_BYTES", "LAYOUT_LIMB29_MONT"]

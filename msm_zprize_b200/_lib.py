@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmsm_b200.so")
 
 # enums (include/msm_b200.h)
-CURVE_BLS12_377_G1, CURVE_PALLAS, CURVE_ED_ON_BLS12_377 = 0, 1, 2
+CURVE_BLS12_377_G1, CURVE_PALLAS, CURVE_ED_ON_BLS12_377, CURVE_BLS12_381_G1 = 0, 1, 2, 3
 FORM_AFFINE_GLV, FORM_PROJECTIVE, FORM_TE_EXTENDED = 0, 1, 2
 LAYOUT_LIMB29_MONT, LAYOUT_LE_BYTES = 0, 1
 E_INVALID, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4

@@ -12,6 +12,7 @@ static const CurveOps* ops_of(int curve) {
     case MSM_CURVE_BLS12_377_G1: return curve_ops_bls377();
     case MSM_CURVE_PALLAS: return curve_ops_pallas();
     case MSM_CURVE_ED_ON_BLS12_377: return curve_ops_ed377();
+    case MSM_CURVE_BLS12_381_G1: return curve_ops_bls381();
   }
   return nullptr;
 }
@@ -138,7 +139,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   msm_b200_ctx* ctx = nullptr;
   if (!out) return fail(nullptr, MSM_E_INVALID, "null out pointer");
   *out = nullptr;
-  if (curve < 0 || curve > 2) return fail(nullptr, MSM_E_INVALID, "unknown curve");
+  if (curve < 0 || curve > 3) return fail(nullptr, MSM_E_INVALID, "unknown curve");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(nullptr, MSM_E_CUDA, "no such CUDA device");
@@ -320,10 +321,10 @@ int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t
 int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host, const uint32_t* b_host,
                            uint32_t* out_host, size_t n) {
   msm_b200_ctx* ctx = nullptr;
-  if (field < 0 || field > 2 || op < 0 || op > 3 || !a_host || !b_host || !out_host)
+  if (field < 0 || field > 3 || op < 0 || op > 3 || !a_host || !b_host || !out_host)
     return fail(nullptr, MSM_E_INVALID, "bad arguments");
   CK(cudaSetDevice(device));
-  int N = field == 0 ? 12 : 8;
+  int N = (field == 0 || field == 3) ? 12 : 8;
   size_t bytes = n * N * 4;
   uint32_t *a, *b, *o;
   CK(cudaMalloc(&a, bytes));
@@ -334,7 +335,8 @@ int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host
   unsigned grid = cdiv(n, 64);
   if (field == 0) k_test_field<Bls377Fq><<<grid, 64>>>(op, a, b, o, n);
   else if (field == 1) k_test_field<PallasFp><<<grid, 64>>>(op, a, b, o, n);
-  else k_test_field<Bls377Fr><<<grid, 64>>>(op, a, b, o, n);
+  else if (field == 2) k_test_field<Bls377Fr><<<grid, 64>>>(op, a, b, o, n);
+  else k_test_field<Bls381Fq><<<grid, 64>>>(op, a, b, o, n);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out_host, o, bytes, cudaMemcpyDeviceToHost));
   cudaFree(a);
@@ -349,7 +351,7 @@ int msm_b200_test_digits(msm_b200_ctx* ctx, const void* scalars_host, size_t n, 
   if (ctx->curve == MSM_CURVE_ED_ON_BLS12_377) return fail(ctx, MSM_E_INVALID, "GLV digits need a Weierstrass curve");
   CK(cudaSetDevice(ctx->device));
   int c = window_bits > 0 ? window_bits : 13;
-  int b = ctx->curve == MSM_CURVE_BLS12_377_G1 ? 126 : 127;
+  int b = ctx->curve == MSM_CURVE_BLS12_377_G1 ? 126 : 127;  // Scalar.maxBits of the GLV curves
   int K = (b + 1 + c - 1) / c;
   uint32_t* d_dig;
   CK(cudaMalloc(&d_dig, 2 * n * K * 4));

@@ -144,9 +144,10 @@ struct Timer {
 // ------------------------------------------------------------------------------------------
 // curve dispatch helpers
 // ------------------------------------------------------------------------------------------
-static int field_limbs(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 12 : 8; }
-static int field_limbs29(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 14 : 9; }
-static int field_bytes(int curve) { return curve == MSM_CURVE_BLS12_377_G1 ? 48 : 32; }
+static bool field_is_large(int curve) { return curve == MSM_CURVE_BLS12_377_G1 || curve == MSM_CURVE_BLS12_381_G1; }
+static int field_limbs(int curve) { return field_is_large(curve) ? 12 : 8; }
+static int field_limbs29(int curve) { return field_is_large(curve) ? 14 : 9; }
+static int field_bytes(int curve) { return field_is_large(curve) ? 48 : 32; }
 
 static size_t point_bytes(int curve, int layout) {
   if (layout == MSM_LAYOUT_LE_BYTES) return 2 * (size_t)field_bytes(curve);
@@ -369,7 +370,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
                           msm_b200_timing* tm, uint32_t* digits_dump_dev) {
   constexpr size_t FE = F::N * 4;
   Timer T(ctx);
-  const int b = G::QBITS == 253 ? 126 : 127;  // Scalar.maxBits, src/wasm/glv.ts:216-226
+  const int b = G::MAXBITS;  // Scalar.maxBits, src/wasm/glv.ts:216-226
   const int K = (b + 1 + c - 1) / c;
   const uint32_t L = 1u << (c - 1);
   const size_t NB = (size_t)K * L;
@@ -556,6 +557,7 @@ struct CurveOps {
 const CurveOps* curve_ops_bls377();
 const CurveOps* curve_ops_pallas();
 const CurveOps* curve_ops_ed377();
+const CurveOps* curve_ops_bls381();
 
 template <class C>
 static int zero_partial_t(msm_b200_ctx* ctx) {

@@ -90,6 +90,7 @@ int ht_fe_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* 
     case 0: return fe_op<Bls377Fq>(op, a, b, out);
     case 1: return fe_op<PallasFp>(op, a, b, out);
     case 2: return fe_op<Bls377Fr>(op, a, b, out);
+    case 3: return fe_op<Bls381Fq>(op, a, b, out);
   }
   return -1;
 }
@@ -97,6 +98,7 @@ int ht_proj_op(int field, int op, const uint32_t* p, const uint32_t* q, uint32_t
   switch (field) {
     case 0: return proj_op<Bls377Fq, 3>(op, p, q, out);
     case 1: return proj_op<PallasFp, 15>(op, p, q, out);
+    case 3: return proj_op<Bls381Fq, 12>(op, p, q, out);
   }
   return -1;
 }
@@ -104,6 +106,7 @@ int ht_aff_op(int field, int flags, const uint32_t* p, const uint32_t* q, uint32
   switch (field) {
     case 0: return aff_op<Bls377Fq>(flags, p, q, out);
     case 1: return aff_op<PallasFp>(flags, p, q, out);
+    case 3: return aff_op<Bls381Fq>(flags, p, q, out);
   }
   return -1;
 }
@@ -115,6 +118,7 @@ int ht_glv(int curve, const uint32_t* s, uint32_t* s0, uint32_t* s1) {
   for (int i = 0; i < 8; i++) t[i] = s[i];
   if (curve == 0) { scalar_reduce<Bls377Glv>(t); return (int)glv_decompose<Bls377Glv>(t, s0, s1); }
   if (curve == 1) { scalar_reduce<PallasGlv>(t); return (int)glv_decompose<PallasGlv>(t, s0, s1); }
+  if (curve == 3) { scalar_reduce<Bls381Glv>(t); return (int)glv_decompose<Bls381Glv>(t, s0, s1); }
   return -1;
 }
 }

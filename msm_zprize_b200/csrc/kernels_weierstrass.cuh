@@ -29,7 +29,7 @@ constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree l
 constexpr int TREE_MAX = 65536;   // serial levels until at most this many elements remain
 constexpr int MAX_ROUNDS = 30;
 constexpr int N_TOTALS = 2 * MAX_ROUNDS + 8;  // see k_scan
-constexpr int FINISH_MAX = 16384;  // finish the tree per bucket once at most this many pair slots are left
+constexpr int FINISH_MAX = 32768;  // finish the tree per bucket once at most this many pair slots are left
 
 // ------------------------------------------------------------------------------------------
 // ingest

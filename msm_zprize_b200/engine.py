@@ -16,8 +16,8 @@ import numpy as np
 from . import _lib as L
 
 CURVES = {"bls12-377": L.CURVE_BLS12_377_G1, "pallas": L.CURVE_PALLAS,
-          "ed-on-bls12-377": L.CURVE_ED_ON_BLS12_377}
-FIELD_BYTES = {L.CURVE_BLS12_377_G1: 48, L.CURVE_PALLAS: 32, L.CURVE_ED_ON_BLS12_377: 32}
+          "ed-on-bls12-377": L.CURVE_ED_ON_BLS12_377, "bls12-381": L.CURVE_BLS12_381_G1}
+FIELD_BYTES = {L.CURVE_BLS12_377_G1: 48, L.CURVE_PALLAS: 32, L.CURVE_ED_ON_BLS12_377: 32, L.CURVE_BLS12_381_G1: 48}
 
 
 @dataclass

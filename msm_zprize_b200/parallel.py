@@ -101,8 +101,8 @@ class CurveBundle:
 
 
 def create_weierstrass(name: str, device: int = 0) -> CurveBundle:
-    """Weierstrass.create(params) (src/parallel.ts:40-177) for "bls12-377" or "pallas"."""
-    assert name in ("bls12-377", "pallas")
+    """Weierstrass.create(params) (src/parallel.ts:40-177) for "bls12-377", "pallas" or "bls12-381"."""
+    assert name in ("bls12-377", "pallas", "bls12-381")
     return CurveBundle(name, device)
 
 

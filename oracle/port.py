@@ -42,7 +42,7 @@ def _set(field, value: int):
 
 
 class Port:
-    """One curve of the CPU port.  curve: 'bls12-377' | 'pallas' | 'ed-on-bls12-377'."""
+    """One curve of the CPU port.  curve: 'bls12-377' | 'pallas' | 'bls12-381' | 'ed-on-bls12-377'."""
 
     def __init__(self, curve: str):
         self.L = _lib()
@@ -55,7 +55,7 @@ class Port:
             self.nbytes, n29 = 32, O.montgomery_params(P.p).n
             self.field_bits = O.log2(P.p)
         else:
-            P = O.BLS12_377 if curve == "bls12-377" else O.PALLAS
+            P = {"bls12-377": O.BLS12_377, "pallas": O.PALLAS, "bls12-381": O.BLS12_381}[curve]
             g = O.glv_params(P.q, P.lam)
             _set(pp.p, P.p), _set(pp.q, P.q), _set(pp.beta, P.beta)
             for k in ("v00", "v01", "v10", "v11", "m0", "m1"):
@@ -64,7 +64,7 @@ class Port:
                 setattr(pp, k + "_neg", 1 if v < 0 else 0)
             pp.glv_m, pp.glv_k, pp.glv_max_bits = g.m, g.k, g.max_bits
             pp.scalar_bits, pp.is_te, pp.b3 = O.log2(P.q), 0, 3 * P.b
-            self.nbytes, n29 = (48 if curve == "bls12-377" else 32), O.montgomery_params(P.p).n
+            self.nbytes, n29 = (32 if curve == "pallas" else 48), O.montgomery_params(P.p).n
             self.field_bits = O.log2(P.p)
         self.q = P.q
         self.h = self.L.port_create(C.byref(pp), n29)

@@ -25,11 +25,11 @@ def _gen(eng, mz, n, seed):
     return d_pts, d_sc, pts, sc
 
 
-@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)])
+@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS), ("bls12-381", O.BLS12_381)])
 def test_generated_weierstrass_inputs(mz, name, params):
     # src/curve-projective.test.ts / curve-twisted-edwards.test.ts:162-198: on curve, in subgroup
     aff = O.WeierstrassAffine(params)
-    n, nb = 200, (48 if name == "bls12-377" else 32)
+    n, nb = 200, (32 if name == "pallas" else 48)
     with mz.MsmEngine(name) as eng:
         d_pts, d_sc, pts, sc = _gen(eng, mz, n, 11)
         P = [(int.from_bytes(pts[i * 2 * nb:i * 2 * nb + nb], "little"),
@@ -60,7 +60,7 @@ def test_generated_te_inputs(mz):
         assert (res.x, res.y) == te.to_affine(O.msm(te, S, [te.from_affine(p) for p in P]))
 
 
-@pytest.mark.parametrize("name,lg", [("bls12-377", 16), ("pallas", 16), ("ed-on-bls12-377", 16)])
+@pytest.mark.parametrize("name,lg", [("bls12-377", 16), ("pallas", 16), ("ed-on-bls12-377", 16), ("bls12-381", 15)])
 def test_large_n_properties(mz, name, lg):
     """n = 2^16: (i) the result does not depend on the window size, (ii) linearity:
     MSM(s, G) == MSM(s[:h], G[:h]) + MSM(s[h:], G[h:]) via run_partial + combine (the multi-GPU path),

@@ -18,9 +18,9 @@ def mz():
     return m
 
 
-FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8)}
+FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8), 3: (O.BLS12_381.p, 12)}
 # internal Montgomery radix R = 2^(32 N)  (fp.cuh fe_mul)
-RBITS = {0: 384, 1: 256, 2: 256}
+RBITS = {0: 384, 1: 256, 2: 256, 3: 384}
 
 
 def _limbs(vals, n):
@@ -31,7 +31,7 @@ def _vals(arr):
     return [sum(int(w) << (32 * i) for i, w in enumerate(row)) for row in arr]
 
 
-@pytest.mark.parametrize("field", [0, 1, 2])
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
 def test_field_ops_on_device(mz, field):
     # src/field.test.ts:15-155 -- multiply / add / subtract / inverse against BigInt
     from msm_zprize_b200.engine import test_field_op
@@ -73,7 +73,7 @@ def test_glv_digits_on_device(mz, name, params, c):
 def _check_weierstrass(mz, name, params, scalars, points, layout="le", form=None, c=0, unreduced=None):
     aff = O.WeierstrassAffine(params)
     n = len(scalars)
-    nb = 48 if name == "bls12-377" else 32
+    nb = 32 if name == "pallas" else 48
     want = O.msm(aff, scalars, points) if n else None
     with mz.MsmEngine(name) as eng:
         if layout == "le":
@@ -114,7 +114,7 @@ def test_kat_bls12_377(mz):
     assert (r2.x, r2.y) == aff.scale(sum(sc) % q, KAT_BLS_P)
 
 
-@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)])
+@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS), ("bls12-381", O.BLS12_381)])
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 16, 64, 257, 1024])
 def test_msm_weierstrass_sizes(mz, name, params, n):
     # src/msm.test.ts:35-83: N = 2^0 .. 2^12 (the oracle here is python: up to 2^10)

@@ -20,9 +20,9 @@ def lib():
     return ctypes.CDLL(LIB)
 
 
-FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8)}
+FIELDS = {0: (O.BLS12_377.p, 12), 1: (O.PALLAS.p, 8), 2: (O.ED_ON_BLS12_377.p, 8), 3: (O.BLS12_381.p, 12)}
 # internal Montgomery radix R = 2^(32 N)  (fp.cuh fe_mul)
-RBITS = {0: 384, 1: 256, 2: 256}
+RBITS = {0: 384, 1: 256, 2: 256, 3: 384}
 
 
 def limbs(x, n):
@@ -60,7 +60,7 @@ def fe_op(lib, field, op, a, b=0):
     return val(out)
 
 
-@pytest.mark.parametrize("field", [0, 1, 2])
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
 def test_field_ops(lib, field):
     p, n = FIELDS[field]
     R = 1 << RBITS[field]
@@ -85,7 +85,7 @@ def test_field_ops(lib, field):
         assert fe_op(lib, field, 8, a) == pow(a, -1, p) * R * R % p
 
 
-@pytest.mark.parametrize("field,params,b3", [(0, O.BLS12_377, 3), (1, O.PALLAS, 15)])
+@pytest.mark.parametrize("field,params,b3", [(0, O.BLS12_377, 3), (1, O.PALLAS, 15), (3, O.BLS12_381, 12)])
 def test_projective_complete_formulas(lib, field, params, b3):
     p, n = FIELDS[field]
     aff = O.WeierstrassAffine(params)
@@ -125,7 +125,7 @@ def test_projective_complete_formulas(lib, field, params, b3):
             assert (unmont(val(out[0:n]), p, n), unmont(val(out[n:2 * n]), p, n)) == P
 
 
-@pytest.mark.parametrize("field,params", [(0, O.BLS12_377), (1, O.PALLAS)])
+@pytest.mark.parametrize("field,params", [(0, O.BLS12_377), (1, O.PALLAS), (3, O.BLS12_381)])
 def test_affine_add_cases(lib, field, params):
     p, n = FIELDS[field]
     aff = O.WeierstrassAffine(params)
@@ -178,7 +178,7 @@ def test_twisted_edwards_formulas(lib):
             assert te.to_affine(dec(out)) == te.to_affine(te.add(P, te.negate(Q)))
 
 
-@pytest.mark.parametrize("curve,params", [(0, O.BLS12_377), (1, O.PALLAS)])
+@pytest.mark.parametrize("curve,params", [(0, O.BLS12_377), (1, O.PALLAS), (3, O.BLS12_381)])
 def test_glv_decompose_matches_oracle(lib, curve, params):
     # src/glv/glv-test.ts:83-125 -- device decomposition == BigInt restatement, sample by sample
     g = O.glv_params(params.q, params.lam)

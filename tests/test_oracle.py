@@ -20,7 +20,7 @@ KAT_ED_T = 344608859351517591455048735505939786829621935504946055818209990677796
 
 
 def test_generators_on_curve_and_in_subgroup():
-    for params in (O.BLS12_377, O.PALLAS):
+    for params in (O.BLS12_377, O.PALLAS, O.BLS12_381):
         aff = O.WeierstrassAffine(params)
         assert aff.is_on_curve(aff.one)
         assert aff.is_in_subgroup(aff.one)
@@ -31,7 +31,7 @@ def test_generators_on_curve_and_in_subgroup():
 
 def test_endomorphism_constants():
     # src/concrete/bls12-377.params.ts:47-70 (debug block) and pasta.params.ts:20-35
-    for params in (O.BLS12_377, O.PALLAS):
+    for params in (O.BLS12_377, O.PALLAS, O.BLS12_381):
         aff = O.WeierstrassAffine(params)
         assert pow(params.lam, 3, params.q) == 1 and params.lam != 1
         assert pow(params.beta, 3, params.p) == 1 and params.beta != 1

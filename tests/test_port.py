@@ -6,11 +6,11 @@ from oracle.port import Port
 from tests import inputs as I
 
 
-@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)])
+@pytest.mark.parametrize("name,params", [("bls12-377", O.BLS12_377), ("pallas", O.PALLAS), ("bls12-381", O.BLS12_381)])
 @pytest.mark.parametrize("n,threads,c", [(1, 1, 0), (2, 1, 3), (17, 3, 4), (64, 4, 0), (300, 8, 6)])
 def test_port_weierstrass(name, params, n, threads, c):
     aff = O.WeierstrassAffine(params)
-    nb = 48 if name == "bls12-377" else 32
+    nb = 32 if name == "pallas" else 48
     pts = O.random_points_weierstrass(aff, n, seed=n)
     sc = O.random_scalars(n, params.q, seed=7 + n)
     want = O.msm(aff, sc, pts)

@@ -20,6 +20,12 @@ PALLAS_P = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001
 PALLAS_Q = 0x40000000000000000000000000000000224698FC0994A8DD8C46EB2100000001
 PALLAS_LAMBDA = pow(5, (PALLAS_Q - 1) // 3, PALLAS_Q)
 PALLAS_BETA = pow(pow(5, (PALLAS_P - 1) // 3, PALLAS_P), 2, PALLAS_P)
+BLS381_P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+BLS381_R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+BLS381_LAMBDA = 0xD201000000010000 ** 2 - 1
+BLS381_BETA = 0x1A0111EA397FE699EC02408663D4DE85AA0D857D89759AD4897D29650FB85F9B409427EB4F49FFFD8BFD00000000AAAC
+BLS381_GX = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
+BLS381_GY = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
 ED_P = BLS377_R
 ED_Q = 0x4AAD957A68B2955982D1347970DEC005293A3AFC43C8AFEB95AEE9AC33FD9FF
 ED_D = 3021
@@ -111,7 +117,21 @@ def glv_struct(name, q, lam):
     m0 = tdiv((1 << (m + k)) * -v11, det)
     m1 = tdiv((1 << (m + k)) * v10, det)
     assert (v00 + lam * v10) % q == 0 and (v01 + lam * v11) % q == 0
+    # upper bound on the half scalars (src/wasm/glv.ts:216-226), in exact rationals
+    from fractions import Fraction as Fr
+
+    def js_rem(a, b):
+        return a - tdiv(a, b) * b
+    m0e = abs(Fr(js_rem((1 << (m + k)) * -v11, det), det))
+    m1e = abs(Fr(js_rem((1 << (m + k)) * v10, det), det))
+    x0e = Fr(1, 2) + Fr(m0, 1 << m) + m0e * Fr(q, 1 << (m + k))
+    x1e = Fr(1, 2) + Fr(m1, 1 << m) + m1e * Fr(q, 1 << (m + k))
+    max_s0 = x0e * abs(v00) + x1e * abs(v01)
+    max_s1 = x0e * abs(v10) + x1e * abs(v11)
+    maxbits = max(ceil_log2(int(abs(max_s0)) + 1), ceil_log2(int(abs(max_s1)) + 1))
+    assert maxbits <= 127
     s = "struct %s {\n" % name
+    s += "  static constexpr int MAXBITS = %d;  // Scalar.maxBits\n" % maxbits
     s += "  static constexpr int SHIFT_K = %d;\n  static constexpr int SHIFT_M = %d;\n" % (k, m)
     s += "  static constexpr int QBITS = %d;\n" % ceil_log2(q)
     for nm, v in (("M0", m0), ("M1", m1)):
@@ -132,8 +152,10 @@ def main():
     out += field_struct("Bls377Fq", BLS377_P, 12, {"BETA": BLS377_BETA, "GX": BLS377_GX, "GY": BLS377_GY})
     out += field_struct("PallasFp", PALLAS_P, 8, {"BETA": PALLAS_BETA, "GX": PALLAS_GX, "GY": PALLAS_GY})
     out += field_struct("Bls377Fr", ED_P, 8, {"K2D": 2 * ED_D % ED_P, "GX": ED_GX, "GY": ED_GY})
+    out += field_struct("Bls381Fq", BLS381_P, 12, {"BETA": BLS381_BETA, "GX": BLS381_GX, "GY": BLS381_GY})
     out += glv_struct("Bls377Glv", BLS377_R, BLS377_LAMBDA)
     out += glv_struct("PallasGlv", PALLAS_Q, PALLAS_LAMBDA)
+    out += glv_struct("Bls381Glv", BLS381_R, BLS381_LAMBDA)
     out += "struct EdScalar {\n  static constexpr int QBITS = %d;\n" % ceil_log2(ED_Q)
     out += arr("Q", limbs(ED_Q, 8)) + "};\n\n"
     out += "}  // namespace msm\n"
