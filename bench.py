@@ -38,7 +38,7 @@ CURVES = {"bls12-377": (48, 12, 126), "pallas": (32, 8, 127), "ed-on-bls12-377":
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--curve", default="bls12-377", choices=list(CURVES))

@@ -159,11 +159,12 @@ static size_t scalar_bytes(int layout) { return layout == MSM_LAYOUT_LE_BYTES ? 
 // Engine default window size (the reference's table is tuned for 16 CPU threads,
 // src/msm-common.ts:33-57; any c gives the same result).  The GPU wants windows that divide the
 // scalar length evenly -- a short top window concentrates all its entries in a few buckets and
-// costs extra tree rounds -- so: GLV halves (127/128 bits) use c = 16 (K = 8) from 2^14 points up,
+// costs extra tree rounds -- so: GLV halves (127/128 bits) use c = 16 (K = 8) from 2^14 points up
+// (c = 19, K = 7 from 2^25: 12 % fewer additions outweigh the larger counting sort there),
 // full-width scalars (252..256 bits) c = 14 / 16 / 18.
 static int default_window(int curve, int form, size_t n) {
   int lg = ceil_log2_sz(n);
-  if (form == MSM_FORM_AFFINE_GLV) return lg >= 14 ? 16 : (lg >= 7 ? 8 : 4);
+  if (form == MSM_FORM_AFFINE_GLV) return lg >= 25 ? 19 : (lg >= 14 ? 16 : (lg >= 7 ? 8 : 4));
   if (curve == MSM_CURVE_ED_ON_BLS12_377) return lg >= 21 ? 18 : (lg >= 13 ? 14 : (lg >= 7 ? 9 : 4));
   return lg >= 13 ? 16 : (lg >= 7 ? 8 : 4);
 }
@@ -434,7 +435,10 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->pairkey[1], (ctx->h_totals[1] + 1) * 4));
   sa.ent = (uint32_t*)ctx->ent.p;
   sa.pairkey = (uint32_t*)ctx->pairkey[0].p;
+  CK(cudaMemsetAsync(ctx->ent.p, 0, (2 * P0 + 2) * 4, ctx->stream));  // padding slots are read (and discarded)
   LAUNCH(ctx, k_hist_scatter<true>, cdiv(S, 256), 256, sa);
+  LAUNCH(ctx, k_fill_pairkey, cdiv((NB + 31) / 32 * 32, 256), 256, (const uint32_t*)ctx->po.p, (uint32_t)NB, (uint32_t)P0,
+         (uint32_t*)ctx->pairkey[0].p);
   int e2 = T.mark();
   // --- tree rounds
   RET_IF(ensure(ctx, ctx->elem[0], ElemBuf<F>::bytes(ctx->h_totals[1] + 1)));
@@ -470,7 +474,8 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.invtot = nullptr;
     a.M1 = 0;
     a.B0 = 0;
-    if (P <= (size_t)FINISH_MAX) {  // tail: one thread per unfinished bucket
+    // tail: one thread per unfinished bucket -- only when few pair slots AND few elements per bucket remain
+    if (P <= (size_t)FINISH_MAX && ((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)FINISH_MAX_ELEMS) {
       if (r == 0)
         LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB);
       else

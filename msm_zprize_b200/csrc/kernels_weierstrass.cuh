@@ -29,7 +29,8 @@ constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree l
 constexpr int TREE_MAX = 65536;   // serial levels until at most this many elements remain
 constexpr int MAX_ROUNDS = 30;
 constexpr int N_TOTALS = 2 * MAX_ROUNDS + 8;  // see k_scan
-constexpr int FINISH_MAX = 32768;  // finish the tree per bucket once at most this many pair slots are left
+constexpr int FINISH_MAX = 32768;
+constexpr int FINISH_MAX_ELEMS = 16;  // ... and at most this many elements per bucket  // finish the tree per bucket once at most this many pair slots are left
 
 // ------------------------------------------------------------------------------------------
 // ingest
@@ -169,8 +170,7 @@ __global__ void k_hist_scatter(SortArgs a) {
     } else {
       uint32_t pos = atomicAdd(&a.cursor[b], 1u);
       uint32_t slot = 2u * a.po0[b] + pos;
-      a.ent[slot] = (uint32_t)h | ((carry ^ sign) << 31);
-      a.pairkey[slot >> 1] = b;
+      a.ent[slot] = (uint32_t)h | ((carry ^ sign) << 31);  // (pairkey is filled by k_fill_pairkey)
     }
   }
 }
@@ -242,6 +242,25 @@ static __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict
   }
 }
 
+// pairkey[i] = bucket of round-0 pair i, written as coalesced runs: one warp per 32 consecutive
+// buckets, lanes stride over each bucket's pair range (replaces a second scattered 4-byte write per
+// entry in the scatter pass).
+static __global__ void __launch_bounds__(256) k_fill_pairkey(const uint32_t* __restrict__ po0, uint32_t NB,
+                                                            uint32_t P0, uint32_t* __restrict__ pairkey) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b0 = warp * 32;
+  if (b0 >= NB) return;
+  const uint32_t mine = (b0 + lane < NB) ? po0[b0 + lane] : P0;  // start of bucket b0 + lane
+  const uint32_t end = (b0 + 32 < NB) ? po0[b0 + 32] : P0;
+#pragma unroll 1
+  for (int src = 0; src < 32; src++) {
+    const uint32_t st = __shfl_sync(0xffffffffu, mine, src);
+    const uint32_t en = (src < 31) ? __shfl_sync(0xffffffffu, mine, (src + 1) & 31) : end;
+    for (uint32_t i = st + lane; i < en; i += 32) pairkey[i] = b0 + src;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // one round of the pairwise tree
 // ------------------------------------------------------------------------------------------
@@ -287,21 +306,27 @@ struct RoundArgs {
   int B0;                // pairs per thread: a block owns ACC_THREADS * B0 consecutive pairs
 };
 
+// Loads of one pair.  Everything that depends only on the pair index (the two elements, or the two
+// sorted entries and then the gathered base points) is issued BEFORE the bucket lookups
+// (pairkey -> po_r / cnt), so a pair costs two dependent memory round trips instead of four.  The
+// second slot of a bucket's last pair may be padding: it is read anyway (the slot exists; round-0
+// entry padding is zeroed) and discarded.
 template <class F, bool R0>
 __device__ __forceinline__ void load_pair(const RoundArgs<F>& a, size_t i, Aff<F>& A, Aff<F>& B, uint32_t& b,
                                           uint32_t& j) {
-  b = a.pairkey[i];
-  j = (uint32_t)i - a.po_r[b];
-  uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
-  bool has2 = 2 * j + 1 < n;
   if (R0) {
     uint2 e = reinterpret_cast<const uint2*>(a.ent)[i];
+    b = a.pairkey[i];
     A = gather_base<F>(a.bases, e.x);
-    B = has2 ? gather_base<F>(a.bases, e.y) : aff_inf<F>();
+    B = gather_base<F>(a.bases, e.y);
   } else {
+    b = a.pairkey[i];
     A = a.in.load(2 * i);
-    B = has2 ? a.in.load(2 * i + 1) : aff_inf<F>();
+    B = a.in.load(2 * i + 1);
   }
+  j = (uint32_t)i - a.po_r[b];
+  uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
+  if (!(2 * j + 1 < n)) B = aff_inf<F>();
 }
 
 // Denominator of pair i for the forward pass.  Only the x coordinates are needed unless they are
@@ -309,32 +334,34 @@ __device__ __forceinline__ void load_pair(const RoundArgs<F>& a, size_t i, Aff<F
 // forward pass is HBM-bound (1 modmul per ~150 bytes), the backward pass is not.
 template <class F, bool R0>
 __device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i, Fe<F>& d) {
-  uint32_t b = a.pairkey[i];
+  Fe<F> xa, xb;
+  uint2 e = make_uint2(0u, 0u);
+  uint32_t b;
+  if (R0) {
+    e = reinterpret_cast<const uint2*>(a.ent)[i];
+    b = a.pairkey[i];
+    xa = ld_aos<F>(a.bases + (size_t)ent_index(e.x) * (2 * F::N / 4));
+    xb = ld_aos<F>(a.bases + (size_t)ent_index(e.y) * (2 * F::N / 4));
+  } else {
+    b = a.pairkey[i];
+    xa = ld_soa<F>(a.in.coord(0, 0), a.in.cap, i);
+    xb = ld_soa<F>(a.in.coord(1, 0), a.in.cap, i);
+  }
   uint32_t j = (uint32_t)i - a.po_r[b];
   uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
   if (!(2 * j + 1 < n)) return false;  // single element: passes through
-  Fe<F> xa, xb;
-  const uint4 *pa = nullptr, *pb = nullptr;
+  if (xa.v[F::N - 1] == AFF_INF_MARK || xb.v[F::N - 1] == AFF_INF_MARK) return false;
+  d = fe_sub(xb, xa);
+  if (!fe_is_zero(d)) return true;
+  Aff<F> A, B;
   if (R0) {
-    uint2 e = reinterpret_cast<const uint2*>(a.ent)[i];
-    pa = a.bases + (size_t)ent_index(e.x) * (2 * F::N / 4);
-    pb = a.bases + (size_t)ent_index(e.y) * (2 * F::N / 4);
-    xa = ld_aos<F>(pa);
-    xb = ld_aos<F>(pb);
-    if (xa.v[F::N - 1] == AFF_INF_MARK || xb.v[F::N - 1] == AFF_INF_MARK) return false;
-    d = fe_sub(xb, xa);
-    if (!fe_is_zero(d)) return true;
-    Aff<F> A = gather_base<F>(a.bases, e.x), B = gather_base<F>(a.bases, e.y);
-    return aff_add_prepare(A, B, d) <= AFF_DBL;
+    A = gather_base<F>(a.bases, e.x);
+    B = gather_base<F>(a.bases, e.y);
   } else {
-    xa = ld_soa<F>(a.in.coord(0, 0), a.in.cap, i);
-    xb = ld_soa<F>(a.in.coord(1, 0), a.in.cap, i);
-    if (xa.v[F::N - 1] == AFF_INF_MARK || xb.v[F::N - 1] == AFF_INF_MARK) return false;
-    d = fe_sub(xb, xa);
-    if (!fe_is_zero(d)) return true;
-    Aff<F> A = a.in.load(2 * i), B = a.in.load(2 * i + 1);
-    return aff_add_prepare(A, B, d) <= AFF_DBL;
+    A = a.in.load(2 * i);
+    B = a.in.load(2 * i + 1);
   }
+  return aff_add_prepare(A, B, d) <= AFF_DBL;
 }
 
 // forward pass: exclusive prefix products of the denominators, per thread.
@@ -371,12 +398,13 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
     if (i >= a.P) continue;
     Aff<F> A, B;
     uint32_t b, j;
+    Fe<F> pre = ld_soa<F>(a.prefix, a.P, i);  // (unused garbage for pass-through pairs)
     load_pair<F, R0>(a, i, A, B, b, j);
+    const uint32_t pon = a.po_n[b];
     Fe<F> d;
     int cs = aff_add_prepare(A, B, d);
     Fe<F> id = inv;
     if (cs <= AFF_DBL) {
-      Fe<F> pre = ld_soa<F>(a.prefix, a.P, i);
       id = fe_mul(inv, pre);
       inv = fe_mul(inv, d);
     }
@@ -385,7 +413,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
     if (n <= 2) {  // one element left after this round: the bucket sum
       a.fin.store(b, R);
     } else {
-      size_t e = 2 * (size_t)a.po_n[b] + j;
+      size_t e = 2 * (size_t)pon + j;
       a.out.store(e, R);
       if (!(e & 1)) a.pairkey_next[e >> 1] = b;
     }
