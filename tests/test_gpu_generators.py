@@ -85,3 +85,22 @@ def test_large_n_properties(mz, name, lg):
         eng.run_partial(d_sc + h * 32, n - h, d_part + pbytes, on_device=True)
         c = eng.combine(d_part, 2)
         assert (a.x, a.y, a.is_zero) == (c.x, c.y, c.is_zero)
+
+
+@pytest.mark.parametrize("name,lg", [("bls12-377", 18), ("pallas", 18)])
+def test_full_size_against_cpu_port(mz, name, lg):
+    """BASELINE.json configs[1] size (BLS12-377 G1, n = 2^18): the GPU result must be bit-identical to the
+    multi-threaded C++ port of the reference algorithm on the same inputs (the python oracle is too slow
+    here; the port is pinned to it in tests/test_port.py)."""
+    import os
+    from oracle.port import Port
+    n = 1 << lg
+    with mz.MsmEngine(name) as eng:
+        d_pts, d_sc, pts, sc = _gen(eng, mz, n, 0xB200 + lg)
+        eng.set_bases_device(d_pts, n)
+        got = eng.run(d_sc, n, on_device=True)
+    port = Port(name)
+    threads = os.cpu_count() or 1
+    prep = port.prepare_points(pts, n, threads)
+    x, y, z, _ = port.msm(sc, prep, n, threads)
+    assert (got.x, got.y, got.is_zero) == (x, y, z)
