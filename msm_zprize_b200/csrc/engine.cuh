@@ -41,7 +41,7 @@ struct msm_b200_ctx {
   size_t n_bases = 0;
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
-  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin;
+  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others;
   unsigned long long* h_totals = nullptr;  // pinned
   uint32_t* h_result = nullptr;            // pinned
   std::vector<cudaEvent_t> ev;
@@ -204,7 +204,7 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
     M[ns + 1] = blocks * UP_THREADS;
     ns++;
   }
-  const bool two = M[ns] > (size_t)TREE_CTA;  // scan level below the top block?
+  const bool two = M[ns] > (size_t)TOP_CTA_MAX;  // scan level below the top block?
   const int top = ns + (two ? 1 : 0);
   if (two) M[top] = cdiv(M[ns], TREE_CTA);
   for (int l = 0; l <= top; l++) RET_IF(ensure(ctx, ctx->lvl_pre[l], (M[l] + 1) * FE));
@@ -213,10 +213,14 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
     LAUNCH(ctx, k_up_fwd<F>, cdiv(M[l], (size_t)UP_THREADS * UP_B1), UP_THREADS, (const uint4*)ctx->lvl_tot[l].p, M[l],
            (uint4*)ctx->lvl_pre[l].p, (uint4*)ctx->lvl_tot[l + 1].p, M[l + 1]);
   if (two)
-    LAUNCH(ctx, (k_tree_up<F, false>), (unsigned)M[top], TREE_CTA, (const uint4*)ctx->lvl_tot[ns].p, M[ns],
+    LAUNCH(ctx, (k_tree_up<F, false, TREE_CTA>), (unsigned)M[top], TREE_CTA, (const uint4*)ctx->lvl_tot[ns].p, M[ns],
            (uint4*)ctx->lvl_pre[ns].p, (uint4*)ctx->lvl_tot[top].p, M[top]);
-  LAUNCH(ctx, (k_tree_up<F, true>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top], (uint4*)ctx->lvl_pre[top].p,
-         (uint4*)nullptr, (size_t)0);
+  if (M[top] <= (size_t)TREE_CTA)
+    LAUNCH(ctx, (k_tree_up<F, true, TREE_CTA>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top],
+           (uint4*)ctx->lvl_pre[top].p, (uint4*)nullptr, (size_t)0);
+  else
+    LAUNCH(ctx, (k_tree_up<F, true, TOP_CTA_MAX>), 1, TOP_CTA_MAX, (const uint4*)ctx->lvl_tot[top].p, M[top],
+           (uint4*)ctx->lvl_pre[top].p, (uint4*)nullptr, (size_t)0);
   if (two)
     LAUNCH(ctx, k_tree_down<F>, (unsigned)M[top], TREE_CTA, (uint4*)ctx->lvl_pre[ns].p, M[ns],
            (const uint4*)ctx->lvl_pre[top].p, M[top]);
@@ -474,6 +478,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.invtot = nullptr;
     a.M1 = 0;
     a.B0 = 0;
+    a.blktot = nullptr;
     // tail: one thread per unfinished bucket -- only when few pair slots AND few elements per bucket remain
     if (P <= (size_t)FINISH_MAX && ((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)FINISH_MAX_ELEMS) {
       if (r == 0)
@@ -497,22 +502,42 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.B0 = B0;
     unsigned grid = cdiv(P, (size_t)ACC_THREADS * B0);
     size_t M1 = (size_t)grid * ACC_THREADS;
-    RET_IF(ensure(ctx, ctx->lvl_tot[0], M1 * FE));
-    RET_IF(ensure(ctx, ctx->lvl_pre[0], M1 * FE));
+    const bool blk = grid <= (unsigned)TOP_CTA_MAX;  // block totals go straight to the top block
     a.prefix = (uint4*)ctx->prefix.p;
-    a.tot = (uint4*)ctx->lvl_tot[0].p;
-    a.invtot = (const uint4*)ctx->lvl_pre[0].p;
     a.M1 = M1;
-    if (r == 0)
-      LAUNCH(ctx, (k_fwd<F, true>), grid, ACC_THREADS, a);
-    else
-      LAUNCH(ctx, (k_fwd<F, false>), grid, ACC_THREADS, a);
-    RET_IF(invert_totals<F>(ctx, M1));
+    size_t Mtree;
+    if (blk) {
+      RET_IF(ensure(ctx, ctx->others, M1 * FE));
+      RET_IF(ensure(ctx, ctx->lvl_tot[0], ((size_t)grid + 1) * FE));
+      RET_IF(ensure(ctx, ctx->lvl_pre[0], ((size_t)grid + 1) * FE));
+      a.tot = (uint4*)ctx->others.p;
+      a.blktot = (uint4*)ctx->lvl_tot[0].p;
+      Mtree = grid;
+    } else {
+      RET_IF(ensure(ctx, ctx->lvl_tot[0], (M1 + 1) * FE));
+      RET_IF(ensure(ctx, ctx->lvl_pre[0], (M1 + 1) * FE));
+      a.tot = (uint4*)ctx->lvl_tot[0].p;
+      a.blktot = nullptr;
+      Mtree = M1;
+    }
+    a.invtot = nullptr;  // set after invert_totals (which may grow its buffers)
+    if (r == 0) {
+      if (blk) LAUNCH(ctx, (k_fwd<F, true, true>), grid, ACC_THREADS, a);
+      else LAUNCH(ctx, (k_fwd<F, true, false>), grid, ACC_THREADS, a);
+    } else {
+      if (blk) LAUNCH(ctx, (k_fwd<F, false, true>), grid, ACC_THREADS, a);
+      else LAUNCH(ctx, (k_fwd<F, false, false>), grid, ACC_THREADS, a);
+    }
+    RET_IF(invert_totals<F>(ctx, Mtree));
+    a.invtot = (const uint4*)ctx->lvl_pre[0].p;
     int h0 = T.mark();
-    if (r == 0)
-      LAUNCH(ctx, (k_bwd<F, true>), grid, ACC_THREADS, a);
-    else
-      LAUNCH(ctx, (k_bwd<F, false>), grid, ACC_THREADS, a);
+    if (r == 0) {
+      if (blk) LAUNCH(ctx, (k_bwd<F, true, true>), grid, ACC_THREADS, a);
+      else LAUNCH(ctx, (k_bwd<F, true, false>), grid, ACC_THREADS, a);
+    } else {
+      if (blk) LAUNCH(ctx, (k_bwd<F, false, true>), grid, ACC_THREADS, a);
+      else LAUNCH(ctx, (k_bwd<F, false, false>), grid, ACC_THREADS, a);
+    }
     int h1 = T.mark();
     hot.push_back({h0, h1});
     n_adds += ctx->h_totals[MAX_ROUNDS + 3 + r];  // additions finished by this k_bwd launch

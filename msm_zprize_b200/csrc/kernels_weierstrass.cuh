@@ -26,6 +26,7 @@ constexpr int UP_THREADS = 64;    // block size of the serial product-tree level
 constexpr int UP_B1 = 8;          // elements per thread, serial levels
 constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree levels (one block per SM:
                                   // a modmul step costs 0.62 us x warps per sub-partition)
+constexpr int TOP_CTA_MAX = 512;   // the top block handles up to this many elements
 constexpr int TREE_MAX = 65536;   // serial levels until at most this many elements remain
 constexpr int MAX_ROUNDS = 30;
 constexpr int N_TOTALS = 2 * MAX_ROUNDS + 8;  // see k_scan
@@ -300,11 +301,97 @@ struct RoundArgs {
   FinBuf<F> fin;         // buckets that are down to one element
   // batch inversion, level 0
   uint4* prefix;         // P elements, stride = P
-  uint4* tot;            // one per thread, stride = M1
-  const uint4* invtot;   // inverse of tot, same layout
+  uint4* tot;            // one per thread, stride = M1: the thread's total (BLK: product of the OTHER
+                         //   threads' totals of its block)
+  const uint4* invtot;   // inverse of tot, same layout (BLK: inverse of the block totals, one per block)
+  uint4* blktot;         // BLK: one per block, stride = gridDim.x
   size_t M1;
   int B0;                // pairs per thread: a block owns ACC_THREADS * B0 consecutive pairs
 };
+
+// ---- scan-based top of the product tree (latency: ~25 dependent modmuls for a 1024x reduction
+// instead of 3 per element in a serial chain) ------------------------------------------------
+template <class F>
+__device__ __forceinline__ Fe<F> fe_shfl_up(const Fe<F>& v, int d) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_up_sync(0xffffffffu, v.v[i], d);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_shfl_down(const Fe<F>& v, int d) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_shfl(const Fe<F>& v, int src) {
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void fe_to_smem(uint32_t* s, const Fe<F>& v) {
+#pragma unroll
+  for (int i = 0; i < F::N; i++) s[i] = v.v[i];
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_from_smem(const uint32_t* s) {
+  Fe<F> v;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) v.v[i] = s[i];
+  return v;
+}
+
+// inclusive prefix (p) and suffix (s) products across the lanes of a warp
+template <class F>
+__device__ __forceinline__ void warp_scan_products(const Fe<F>& v, int lane, Fe<F>& p, Fe<F>& s) {
+  p = v;
+  s = v;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Fe<F> tp = fe_shfl_up(p, d), ts = fe_shfl_down(s, d);
+    Fe<F> np = fe_mul(p, tp), ns = fe_mul(s, ts);
+    p = fe_select(lane >= d, np, p);
+    s = fe_select(lane + d < 32, ns, s);
+  }
+}
+
+// Products over a block of NT threads (one value per thread): `others` = product of all the
+// block's values but this thread's, `total` = product of all of them (valid in every thread).
+// ~13 dependent modmuls per thread (two 5-step warp scans + 3) and one more scan in warp 0.
+template <class F, int NT>
+__device__ __forceinline__ void block_products(const Fe<F>& v, Fe<F>& others, Fe<F>& total, uint32_t* smem) {
+  constexpr int NW = NT / 32;
+  uint32_t* wtot = smem;
+  uint32_t* wpre = smem + 32 * F::N;
+  uint32_t* wsuf = smem + 64 * F::N;
+  uint32_t* btot = smem + 96 * F::N;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  Fe<F> p, s;
+  warp_scan_products(v, lane, p, s);
+  if (lane == 31) fe_to_smem<F>(wtot + w * F::N, p);
+  __syncthreads();
+  if (w == 0) {
+    Fe<F> x = (lane < NW) ? fe_from_smem<F>(wtot + lane * F::N) : fe_one<F>(), xp, xs;
+    warp_scan_products(x, lane, xp, xs);
+    Fe<F> pre = fe_shfl_up(xp, 1), suf = fe_shfl_down(xs, 1);
+    if (lane == 0) pre = fe_one<F>();
+    if (lane == 31) suf = fe_one<F>();
+    fe_to_smem<F>(wpre + lane * F::N, pre);
+    fe_to_smem<F>(wsuf + lane * F::N, suf);
+    if (lane == 31) fe_to_smem<F>(btot, xp);
+  }
+  __syncthreads();
+  Fe<F> pe = fe_shfl_up(p, 1), se = fe_shfl_down(s, 1);
+  if (lane == 0) pe = fe_one<F>();
+  if (lane == 31) se = fe_one<F>();
+  others = fe_mul(fe_mul(fe_from_smem<F>(wpre + w * F::N), pe), fe_mul(se, fe_from_smem<F>(wsuf + w * F::N)));
+  total = fe_from_smem<F>(btot);
+}
+constexpr int BLOCK_PRODUCTS_SMEM_WORDS(int n) { return 97 * n; }
 
 // Loads of one pair.  Everything that depends only on the pair index (the two elements, or the two
 // sorted entries and then the gathered base points) is issued BEFORE the bucket lookups
@@ -367,8 +454,11 @@ __device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i,
 // forward pass: exclusive prefix products of the denominators, per thread.
 // A block owns ACC_THREADS * B0 consecutive pairs; thread t takes pairs t, t + 256, ... of them, so
 // every warp access is coalesced.
-template <class F, bool R0>
+// BLK (small rounds): the block multiplies its thread totals on the spot (block_products), so the
+// product tree starts from one element per block and two kernel launches per round disappear.
+template <class F, bool R0, bool BLK>
 __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
+  __shared__ uint32_t smem[BLK ? 97 * F::N : 1];
   const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
   const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
   Fe<F> run = fe_one<F>();
@@ -382,15 +472,23 @@ __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
       run = fe_mul(run, d);
     }
   }
-  st_soa<F>(a.tot, a.M1, gid, run);
+  if (BLK) {
+    Fe<F> others, total;
+    block_products<F, ACC_THREADS>(run, others, total, smem);
+    st_soa<F>(a.tot, a.M1, gid, others);
+    if (threadIdx.x == 0) st_soa<F>(a.blktot, gridDim.x, blockIdx.x, total);
+  } else {
+    st_soa<F>(a.tot, a.M1, gid, run);
+  }
 }
 
 // backward pass: individual inverses from the running inverse, then finish the additions
-template <class F, bool R0>
+template <class F, bool R0, bool BLK>
 __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
   const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
   const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
-  Fe<F> inv = ld_soa<F>(a.invtot, a.M1, gid);
+  Fe<F> inv = BLK ? fe_mul(ld_soa<F>(a.invtot, gridDim.x, blockIdx.x), ld_soa<F>(a.tot, a.M1, gid))
+                  : ld_soa<F>(a.invtot, a.M1, gid);
   // same pairs as the forward pass, in reverse order
 #pragma unroll 1
   for (int s = a.B0 - 1; s >= 0; s--) {
@@ -479,92 +577,26 @@ __global__ void __launch_bounds__(UP_THREADS) k_up_bwd(const uint4* __restrict__
   }
 }
 
-// ---- scan-based top of the product tree (latency: ~25 dependent modmuls for a 1024x reduction
-// instead of 3 per element in a serial chain) ------------------------------------------------
-template <class F>
-__device__ __forceinline__ Fe<F> fe_shfl_up(const Fe<F>& v, int d) {
-  Fe<F> r;
-#pragma unroll
-  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_up_sync(0xffffffffu, v.v[i], d);
-  return r;
-}
-template <class F>
-__device__ __forceinline__ Fe<F> fe_shfl_down(const Fe<F>& v, int d) {
-  Fe<F> r;
-#pragma unroll
-  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
-  return r;
-}
-template <class F>
-__device__ __forceinline__ Fe<F> fe_shfl(const Fe<F>& v, int src) {
-  Fe<F> r;
-#pragma unroll
-  for (int i = 0; i < F::N; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
-  return r;
-}
-template <class F>
-__device__ __forceinline__ void fe_to_smem(uint32_t* s, const Fe<F>& v) {
-#pragma unroll
-  for (int i = 0; i < F::N; i++) s[i] = v.v[i];
-}
-template <class F>
-__device__ __forceinline__ Fe<F> fe_from_smem(const uint32_t* s) {
-  Fe<F> v;
-#pragma unroll
-  for (int i = 0; i < F::N; i++) v.v[i] = s[i];
-  return v;
-}
-
-// inclusive prefix (p) and suffix (s) products across the lanes of a warp
-template <class F>
-__device__ __forceinline__ void warp_scan_products(const Fe<F>& v, int lane, Fe<F>& p, Fe<F>& s) {
-  p = v;
-  s = v;
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    Fe<F> tp = fe_shfl_up(p, d), ts = fe_shfl_down(s, d);
-    Fe<F> np = fe_mul(p, tp), ns = fe_mul(s, ts);
-    p = fe_select(lane >= d, np, p);
-    s = fe_select(lane + d < 32, ns, s);
-  }
-}
-
-// One block handles TREE_CTA elements: `others[i]` = product of all the block's elements but i,
+// One block handles CTA elements: `others[i]` = product of all the block's elements but i,
 // `tot[block]` = product of all of them.  TOP: the block is the whole level; it inverts its total
 // and writes the individual inverses straight to `others`.
-template <class F, bool TOP>
-__global__ void __launch_bounds__(TREE_CTA) k_tree_up(const uint4* __restrict__ val, size_t M, uint4* __restrict__ others,
-                                                      uint4* __restrict__ tot, size_t Mn) {
-  constexpr int NW = TREE_CTA / 32;
-  __shared__ uint32_t wtot[32 * F::N], wpre[32 * F::N], wsuf[32 * F::N], binv[F::N];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const size_t i = (size_t)blockIdx.x * TREE_CTA + t;
+template <class F, bool TOP, int CTA>
+__global__ void __launch_bounds__(CTA) k_tree_up(const uint4* __restrict__ val, size_t M, uint4* __restrict__ others,
+                                                 uint4* __restrict__ tot, size_t Mn) {
+  __shared__ uint32_t smem[97 * F::N + F::N];
+  const size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
   Fe<F> v = (i < M) ? ld_soa<F>(val, M, i) : fe_one<F>();
-  Fe<F> p, s;
-  warp_scan_products(v, lane, p, s);
-  if (lane == 31) fe_to_smem<F>(wtot + w * F::N, p);
-  __syncthreads();
-  if (w == 0) {
-    Fe<F> x = (lane < NW) ? fe_from_smem<F>(wtot + lane * F::N) : fe_one<F>(), xp, xs;
-    warp_scan_products(x, lane, xp, xs);
-    Fe<F> pre = fe_shfl_up(xp, 1), suf = fe_shfl_down(xs, 1);
-    if (lane == 0) pre = fe_one<F>();
-    if (lane == 31) suf = fe_one<F>();
-    fe_to_smem<F>(wpre + lane * F::N, pre);
-    fe_to_smem<F>(wsuf + lane * F::N, suf);
-    if (lane == 31) {
-      if (TOP)
-        fe_to_smem<F>(binv, fe_inv(xp));
-      else
-        st_soa<F>(tot, Mn, blockIdx.x, xp);
-    }
+  Fe<F> o, total;
+  block_products<F, CTA>(v, o, total, smem);
+  if (TOP) {
+    uint32_t* binv = smem + 97 * F::N;
+    __syncthreads();
+    if (threadIdx.x == 0) fe_to_smem<F>(binv, fe_inv(total));
+    __syncthreads();
+    o = fe_mul(o, fe_from_smem<F>(binv));
+  } else if (threadIdx.x == 0) {
+    st_soa<F>(tot, Mn, blockIdx.x, total);
   }
-  __syncthreads();
-  Fe<F> pe = fe_shfl_up(p, 1), se = fe_shfl_down(s, 1);
-  if (lane == 0) pe = fe_one<F>();
-  if (lane == 31) se = fe_one<F>();
-  Fe<F> o = fe_mul(fe_mul(fe_from_smem<F>(wpre + w * F::N), pe), fe_mul(se, fe_from_smem<F>(wsuf + w * F::N)));
-  if (TOP) o = fe_mul(o, fe_from_smem<F>(binv));
   if (i < M) st_soa<F>(others, M, i, o);
 }
 
