@@ -249,10 +249,16 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   remaining -= gb;
   int cur = 0;
   while (remaining > 0) {
-    gb = remaining < 5 ? remaining : 5;  // one item per lane, groups of 2^gb lanes
+    if (items > 4096) {
+      gb = remaining < 5 ? remaining : 5;  // throughput-bound level: one item per lane, groups of 2^gb lanes
+      LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
+             (uint4*)ctx->red[cur ^ 1].p);
+    } else {
+      gb = remaining < 3 ? remaining : 3;  // latency-bound level: one item per lane quad
+      LAUNCH(ctx, (k_reduce_quad<C>), cdiv(items * 4, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
+             (uint4*)ctx->red[cur ^ 1].p);
+    }
     size_t out_items = items >> gb;
-    LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
-           (uint4*)ctx->red[cur ^ 1].p);
     items = out_items;
     remaining -= gb;
     cur ^= 1;

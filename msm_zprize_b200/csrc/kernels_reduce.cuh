@@ -312,6 +312,44 @@ __global__ void __launch_bounds__(64) k_reduce_warp(const uint4* __restrict__ in
   }
 }
 
+// Same weighted-sum level as k_reduce_warp, but every item is held by a lane QUAD that shares the
+// field products of each complete addition (latency-bound levels with few items: 3 bits per level,
+// (3 + 1 + 3) additions of ~4.5 us instead of (5 + 1 + 5) of ~8.7 us).
+template <class C>
+__global__ void __launch_bounds__(64) k_reduce_quad(const uint4* __restrict__ in, uint32_t n_items, int gb,
+                                                    uint4* __restrict__ out) {
+  typedef typename C::Acc Acc;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t >> 2;  // item
+  const int g = 1 << gb;      // items per group, g <= 8 (a group spans 4 g <= 32 lanes)
+  const int j = (int)(i & (uint32_t)(g - 1));
+  const bool live = i < n_items;
+  const uint4* p = in + (size_t)(live ? i : 0) * item_u4<C>();
+  Acc S = live ? C::ld(p) : C::zero();
+  Acc Y = live ? C::ld(p + item_u4<C>() / 2) : C::zero();
+#pragma unroll 1
+  for (int d = 1; d < g; d <<= 1) {
+    Acc n = C::add_quad(S, C::shfl_down(S, 4 * d));
+    if (j + d < g) S = n;
+  }
+  {
+    Acc n = C::add_quad(Y, S);
+    if (j >= 1) Y = n;
+  }
+#pragma unroll 1
+  for (int d = g >> 1; d >= 1; d >>= 1) {
+    Acc n = C::add_quad(Y, C::shfl_down(Y, 4 * d));
+    if (j < d) Y = n;
+  }
+#pragma unroll 1
+  for (int d = 0; d < gb; d++) S = C::dbl_quad(S);
+  if (live && j == 0 && (t & 3) == 0) {
+    uint4* o = out + (size_t)(i >> gb) * item_u4<C>();
+    C::st(o, S);
+    C::st(o + item_u4<C>() / 2, Y);
+  }
+}
+
 // One warp; every lane quad runs the same Horner chain cooperatively (src/msm-batched-affine.ts:310-321).
 template <class C>
 __global__ void __launch_bounds__(32) k_horner(const uint4* __restrict__ items, int K, int c, uint4* __restrict__ partial) {
