@@ -41,7 +41,7 @@ struct msm_b200_ctx {
   size_t n_bases = 0;
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
-  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others;
+  DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others, tilesum;
   unsigned long long* h_totals = nullptr;  // pinned
   uint32_t* h_result = nullptr;            // pinned
   std::vector<cudaEvent_t> ev;
@@ -234,6 +234,19 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
 template <class C>
 static int zero_partial_t(msm_b200_ctx* ctx);
 
+// pair-slot offsets of `rounds` tree rounds (ctx->cnt -> ctx->po, ctx->totals)
+static int launch_scan(msm_b200_ctx* ctx, size_t NB, int rounds) {
+  unsigned ntiles = cdiv(NB, SCAN_TILE);
+  RET_IF(ensure(ctx, ctx->tilesum, (size_t)rounds * ntiles * 4));
+  dim3 grid(ntiles, rounds);
+  LAUNCH(ctx, k_scan_tiles, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->tilesum.p, ntiles,
+         (unsigned long long*)ctx->totals.p);
+  LAUNCH(ctx, k_scan_write, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (const uint32_t*)ctx->tilesum.p,
+         ntiles, (uint32_t*)ctx->po.p, (unsigned long long*)ctx->totals.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // bucket reduction + Horner -> partial result in ctx->partial (any curve form)
 // ------------------------------------------------------------------------------------------
@@ -307,8 +320,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
-  LAUNCH(ctx, k_scan, 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
-         (unsigned long long*)ctx->totals.p);
+  RET_IF(launch_scan(ctx, NB, 1));
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t P0 = ctx->h_totals[0];
@@ -414,8 +426,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   int e1 = T.mark();
   // --- offsets for every round, one host sync
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
-  LAUNCH(ctx, k_scan, MAX_ROUNDS + 1, 1024, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->po.p,
-         (unsigned long long*)ctx->totals.p);
+  RET_IF(launch_scan(ctx, NB, MAX_ROUNDS + 1));
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const unsigned long long maxcnt = ctx->h_totals[MAX_ROUNDS + 1];

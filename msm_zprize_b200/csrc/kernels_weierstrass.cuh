@@ -176,71 +176,112 @@ __global__ void k_hist_scatter(SortArgs a) {
   }
 }
 
-// Block r computes, for tree round r, the exclusive scan over buckets of the pair slots
+// Exclusive scan over buckets of the pair slots, for every tree round r at once (grid.y = round):
 // pairs_r[b] = ceil(n_r[b] / 2) with n_r[b] = ceil(cnt[b] / 2^r) elements left -- but 0 once a bucket
 // is down to one element (r >= 1): its sum then already sits in the `fin` array and it leaves the
-// tree.  Block 0 also computes the max count.
-// po[r * NB + b], totals[r], totals[MAX_ROUNDS+1] = max count, totals[MAX_ROUNDS+2] = sum of counts,
-// totals[MAX_ROUNDS+3+r] = additions performed in round r (sum of floor(n_r / 2) over live buckets).
-// Tiled: 1024 threads x 4 consecutive buckets per tile, warp-shuffle block scan, running offset.
-static __global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ cnt, uint32_t NB,
-                                                     uint32_t* __restrict__ po, unsigned long long* __restrict__ totals) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t tile_total;
-  const int r = blockIdx.x;
+// tree.  Two launches: per-tile sums (SCAN_TILE buckets per block), then every block adds the sums of
+// the tiles before it and rescans its own tile.
+//   po[r * NB + b], totals[r] = pair slots of round r, totals[MAX_ROUNDS+1] = max count,
+//   totals[MAX_ROUNDS+2] = sum of counts, totals[MAX_ROUNDS+3+r] = additions performed in round r.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = SCAN_THREADS * 4;
+
+__device__ __forceinline__ uint32_t scan_pairs_of(uint32_t c0, int r) {
+  uint32_t n = (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r);
+  return (n >= (r == 0 ? 1u : 2u)) ? ((n + 1) >> 1) : 0u;
+}
+
+// block-wide exclusive scan of one value per thread; returns the block total in `total`
+__device__ __forceinline__ uint32_t scan_block_exclusive(uint32_t local, uint32_t& total, uint32_t* wsum) {
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  unsigned long long running = 0, nent = 0, nadd = 0;
-  uint32_t mx = 0;
-  const unsigned long long rnd = (1ull << r) - 1;
-  for (uint32_t base = 0; base < NB; base += 4096) {
-    uint32_t b0 = base + 4 * t;
-    uint32_t v[4];
-    uint32_t local = 0;
+  uint32_t incl = local;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t c0 = (b0 + j < NB) ? cnt[b0 + j] : 0u;
-      mx = max(mx, c0);
-      nent += c0;
-      uint32_t n = (uint32_t)(((unsigned long long)c0 + rnd) >> r);
-      v[j] = (n >= (r == 0 ? 1u : 2u)) ? ((n + 1) >> 1) : 0u;  // a bucket with one element left is done
-      nadd += n >> 1;
-      local += v[j];
-    }
-    // inclusive warp scan of `local`
-    uint32_t incl = local;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = (lane < SCAN_THREADS / 32) ? wsum[lane] : 0u, xi = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
+      uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
+      if (lane >= d) xi += o;
     }
-    if (lane == 31) wsum[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t x = wsum[lane], xi = x;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
-        if (lane >= d) xi += o;
-      }
-      wsum[lane] = xi - x;  // exclusive prefix of the warp sums
-      if (lane == 31) tile_total = xi;
-    }
-    __syncthreads();
-    unsigned long long off = running + wsum[w] + (incl - local);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (b0 + j < NB) po[(size_t)r * NB + b0 + j] = (uint32_t)off;
-      off += v[j];
-    }
-    running += tile_total;
-    __syncthreads();
+    wsum[lane] = xi - x;
+    if (lane == 31) wsum[32] = xi;
   }
-  if (t == 0) totals[r] = running;
-  atomicAdd(&totals[MAX_ROUNDS + 3 + r], nadd);
-  if (r == 0) {
-    atomicMax(&totals[MAX_ROUNDS + 1], (unsigned long long)mx);
-    atomicAdd(&totals[MAX_ROUNDS + 2], nent);
+  __syncthreads();
+  total = wsum[32];
+  return wsum[w] + incl - local;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ cnt, uint32_t NB,
+                                                                   uint32_t* __restrict__ tilesum, uint32_t ntiles,
+                                                                   unsigned long long* __restrict__ totals) {
+  __shared__ uint32_t wsum[33];
+  const int r = blockIdx.y;
+  const uint32_t b0 = blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+  uint32_t local = 0, mx = 0;
+  unsigned long long nent = 0, nadd = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t c0 = (b0 + j < NB) ? cnt[b0 + j] : 0u;
+    mx = max(mx, c0);
+    nent += c0;
+    nadd += (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r) >> 1;
+    local += scan_pairs_of(c0, r);
   }
+  uint32_t total;
+  scan_block_exclusive(local, total, wsum);
+  if (threadIdx.x == 0) tilesum[(size_t)r * ntiles + blockIdx.x] = total;
+  // block-reduce the statistics through the same shared array
+  for (int d = 16; d >= 1; d >>= 1) {
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    nent += __shfl_down_sync(0xffffffffu, nent, d);
+    nadd += __shfl_down_sync(0xffffffffu, nadd, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&totals[MAX_ROUNDS + 3 + r], nadd);
+    if (r == 0) {
+      atomicMax(&totals[MAX_ROUNDS + 1], (unsigned long long)mx);
+      atomicAdd(&totals[MAX_ROUNDS + 2], nent);
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __restrict__ cnt, uint32_t NB,
+                                                                   const uint32_t* __restrict__ tilesum, uint32_t ntiles,
+                                                                   uint32_t* __restrict__ po,
+                                                                   unsigned long long* __restrict__ totals) {
+  __shared__ uint32_t wsum[33];
+  __shared__ unsigned long long sbase;
+  const int r = blockIdx.y;
+  // base = sum of the tile sums before this tile
+  unsigned long long part = 0;
+  for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) part += tilesum[(size_t)r * ntiles + i];
+  for (int d = 16; d >= 1; d >>= 1) part += __shfl_down_sync(0xffffffffu, part, d);
+  if (threadIdx.x == 0) sbase = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sbase, part);
+  __syncthreads();
+  const unsigned long long base = sbase;
+  const uint32_t b0 = blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+  uint32_t v[4], local = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    v[j] = scan_pairs_of((b0 + j < NB) ? cnt[b0 + j] : 0u, r);
+    local += v[j];
+  }
+  uint32_t total;
+  unsigned long long off = base + scan_block_exclusive(local, total, wsum);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (b0 + j < NB) po[(size_t)r * NB + b0 + j] = (uint32_t)off;
+    off += v[j];
+  }
+  if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) totals[r] = base + total;
 }
 
 // pairkey[i] = bucket of round-0 pair i, written as coalesced runs: one warp per 32 consecutive
