@@ -235,14 +235,14 @@ template <class C>
 static int zero_partial_t(msm_b200_ctx* ctx);
 
 // pair-slot offsets of `rounds` tree rounds (ctx->cnt -> ctx->po, ctx->totals)
-static int launch_scan(msm_b200_ctx* ctx, size_t NB, int rounds) {
+static int launch_scan(msm_b200_ctx* ctx, size_t NB, int rounds, uint32_t split = 0) {
   unsigned ntiles = cdiv(NB, SCAN_TILE);
   RET_IF(ensure(ctx, ctx->tilesum, (size_t)rounds * ntiles * 4));
   dim3 grid(ntiles, rounds);
   LAUNCH(ctx, k_scan_tiles, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->tilesum.p, ntiles,
-         (unsigned long long*)ctx->totals.p);
+         (unsigned long long*)ctx->totals.p, split);
   LAUNCH(ctx, k_scan_write, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (const uint32_t*)ctx->tilesum.p,
-         ntiles, (uint32_t*)ctx->po.p, (unsigned long long*)ctx->totals.p);
+         ntiles, (uint32_t*)ctx->po.p, (unsigned long long*)ctx->totals.p, split);
   CK(cudaGetLastError());
   return 0;
 }
@@ -300,7 +300,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   RET_IF(ensure(ctx, ctx->hs, n * 32));
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
-  RET_IF(ensure(ctx, ctx->po, NB * 4));
+  RET_IF(ensure(ctx, ctx->po, 2 * NB * 4));
   RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
   LAUNCH(ctx, k_load_scalars<S>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
@@ -320,7 +320,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
-  RET_IF(launch_scan(ctx, NB, 1));
+  RET_IF(launch_scan(ctx, NB, 2, BUCKET_SPLIT));  // po[0]: padded entry offsets, po[1]: virtual-bucket offsets
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t P0 = ctx->h_totals[0];
@@ -330,9 +330,25 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   int e2 = T.mark();
   RET_IF(ensure(ctx, ctx->buckets, NB * C::ACC_FE * FE));
   RET_IF(wait_for_bases(ctx));
+  const size_t V = ctx->h_totals[1];
+  const bool split = ctx->h_totals[MAX_ROUNDS + 1] > (unsigned long long)BUCKET_SPLIT;
+  if (split) {
+    RET_IF(ensure(ctx, ctx->pairkey[0], (V + 1) * 4));
+    RET_IF(ensure(ctx, ctx->elem[0], (V + 1) * C::ACC_FE * FE));
+    LAUNCH(ctx, k_fill_pairkey, cdiv((NB + 31) / 32 * 32, 256), 256, (const uint32_t*)ctx->po.p + NB, (uint32_t)NB,
+           (uint32_t)V, (uint32_t*)ctx->pairkey[0].p);
+  }
   int h0 = T.mark();
-  LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
-         (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);
+  if (split) {
+    LAUNCH(ctx, k_bucket_acc_v<C>, cdiv(V, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
+           (const uint32_t*)ctx->po.p + NB, (const uint32_t*)ctx->pairkey[0].p, (const uint32_t*)ctx->ent.p,
+           (const uint4*)ctx->bases.p, (uint32_t)V, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->elem[0].p);
+    LAUNCH(ctx, k_bucket_combine<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p + NB,
+           (const uint4*)ctx->elem[0].p, (uint32_t)NB, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->buckets.p);
+  } else {
+    LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
+           (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);
+  }
   int h1 = T.mark();
   CK(cudaGetLastError());
   int e3 = T.mark();

@@ -14,6 +14,8 @@
 
 namespace msm {
 
+constexpr int BUCKET_SPLIT = 128;  // entries per virtual bucket of the generic bucket method
+
 template <class F>
 __global__ void k_te_ingest(const uint8_t* __restrict__ in, size_t n, int layout, uint4* __restrict__ bases) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,6 +86,44 @@ __global__ void __launch_bounds__(128) k_bucket_acc(const uint32_t* __restrict__
     acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
   }
   C::st(buckets + (size_t)b * (C::ACC_FE * C::F::N / 4), acc);
+}
+
+// Load balancing for skewed bucket sizes (short top window, repeated scalars): a bucket with more
+// than `split` entries is cut into virtual buckets of `split` entries (one thread each, k_bucket_acc_v),
+// whose accumulators are then added up per bucket (k_bucket_combine).
+template <class C>
+__global__ void __launch_bounds__(128) k_bucket_acc_v(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ po0,
+                                                      const uint32_t* __restrict__ voff, const uint32_t* __restrict__ vkey,
+                                                      const uint32_t* __restrict__ ent, const uint4* __restrict__ bases,
+                                                      uint32_t V, uint32_t split, uint4* __restrict__ vacc) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  uint32_t b = vkey[v];
+  uint32_t lo = (v - voff[b]) * split;
+  uint32_t hi = min(cnt[b], lo + split);
+  typename C::Acc acc = C::zero();
+  const uint32_t* e = ent + 2 * (size_t)po0[b];
+#pragma unroll 1
+  for (uint32_t j = lo; j < hi; j++) {
+    uint32_t en = e[j];
+    acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
+  }
+  C::st(vacc + (size_t)v * (C::ACC_FE * C::F::N / 4), acc);
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ voff,
+                                                        const uint4* __restrict__ vacc, uint32_t NB, uint32_t split,
+                                                        uint4* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  uint32_t nv = (cnt[b] + split - 1) / split;
+  constexpr int U4 = C::ACC_FE * C::F::N / 4;
+  typename C::Acc acc = C::zero();
+  if (nv) acc = C::ld(vacc + (size_t)voff[b] * U4);
+#pragma unroll 1
+  for (uint32_t s = 1; s < nv; s++) acc = C::add(acc, C::ld(vacc + (size_t)(voff[b] + s) * U4));
+  C::st(buckets + (size_t)b * U4, acc);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -186,7 +186,10 @@ __global__ void k_hist_scatter(SortArgs a) {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_THREADS * 4;
 
-__device__ __forceinline__ uint32_t scan_pairs_of(uint32_t c0, int r) {
+// (`split` > 0, used by the generic bucket method: "round" 1 instead counts the virtual buckets
+//  ceil(cnt / split) that an oversized bucket is cut into.)
+__device__ __forceinline__ uint32_t scan_pairs_of(uint32_t c0, int r, uint32_t split = 0) {
+  if (split && r == 1) return (c0 + split - 1) / split;
   uint32_t n = (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r);
   return (n >= (r == 0 ? 1u : 2u)) ? ((n + 1) >> 1) : 0u;
 }
@@ -219,7 +222,7 @@ __device__ __forceinline__ uint32_t scan_block_exclusive(uint32_t local, uint32_
 
 static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ cnt, uint32_t NB,
                                                                    uint32_t* __restrict__ tilesum, uint32_t ntiles,
-                                                                   unsigned long long* __restrict__ totals) {
+                                                                   unsigned long long* __restrict__ totals, uint32_t split) {
   __shared__ uint32_t wsum[33];
   const int r = blockIdx.y;
   const uint32_t b0 = blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
@@ -231,7 +234,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32
     mx = max(mx, c0);
     nent += c0;
     nadd += (uint32_t)(((unsigned long long)c0 + (1ull << r) - 1) >> r) >> 1;
-    local += scan_pairs_of(c0, r);
+    local += scan_pairs_of(c0, r, split);
   }
   uint32_t total;
   scan_block_exclusive(local, total, wsum);
@@ -254,7 +257,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32
 static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __restrict__ cnt, uint32_t NB,
                                                                    const uint32_t* __restrict__ tilesum, uint32_t ntiles,
                                                                    uint32_t* __restrict__ po,
-                                                                   unsigned long long* __restrict__ totals) {
+                                                                   unsigned long long* __restrict__ totals, uint32_t split) {
   __shared__ uint32_t wsum[33];
   __shared__ unsigned long long sbase;
   const int r = blockIdx.y;
@@ -271,7 +274,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32
   uint32_t v[4], local = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    v[j] = scan_pairs_of((b0 + j < NB) ? cnt[b0 + j] : 0u, r);
+    v[j] = scan_pairs_of((b0 + j < NB) ? cnt[b0 + j] : 0u, r, split);
     local += v[j];
   }
   uint32_t total;

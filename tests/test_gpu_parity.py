@@ -234,3 +234,33 @@ def test_resident_bases_and_fresh_scalars(mz):
         sc = O.random_scalars(50, params.q, seed=600)
         res = eng.run(I.scalars_le(sc), 50)
         assert (res.x, res.y) == O.msm(aff, sc, pts[:50])
+
+
+def test_skewed_scalars_all_equal(mz):
+    """Every point has the same scalar: each window has a single bucket holding all n entries
+    (src/bigint/msm.test.ts:35-57 'same scalar => s * sum(P)').  Exercises the deep pairwise tree of the
+    batched-affine path and the virtual-bucket split of the generic bucket method."""
+    n = 3000
+    for name, params in (("bls12-377", O.BLS12_377), ("pallas", O.PALLAS)):
+        aff = O.WeierstrassAffine(params)
+        pts = O.random_points_weierstrass(aff, n, seed=31)
+        s = O.random_scalars(1, params.q, seed=32)[0]
+        total = None
+        for P in pts:
+            total = aff.add(total, P)
+        want = aff.scale(s, total)
+        nb = 32 if name == "pallas" else 48
+        with mz.MsmEngine(name) as eng:
+            for form in (mz.FORM_AFFINE_GLV, mz.FORM_PROJECTIVE):
+                r = eng.msm(I.scalars_le([s] * n), I.points_le(pts, nb), n, form=form)
+                assert (r.x, r.y) == want, (name, form)
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    pts = O.random_points_te(te, n, seed=33)
+    s = O.random_scalars(1, te.q, seed=34)[0]
+    total = te.zero
+    for P in pts:
+        total = te.add(total, te.from_affine(P))
+    want = te.to_affine(te.scale(s, total))
+    with mz.MsmEngine("ed-on-bls12-377") as eng:
+        r = eng.msm(I.scalars_le([s] * n), I.points_le(pts, 32), n)
+        assert (r.x, r.y) == want
