@@ -161,11 +161,11 @@ static size_t scalar_bytes(int layout) { return layout == MSM_LAYOUT_LE_BYTES ? 
 // scalar length evenly -- a short top window concentrates all its entries in a few buckets and
 // costs extra tree rounds -- so: GLV halves (127/128 bits) use c = 16 (K = 8) from 2^14 points up
 // (c = 19, K = 7 from 2^25: 12 % fewer additions outweigh the larger counting sort there),
-// full-width scalars (252..256 bits) c = 14 / 16 / 18.
+// full-width scalars c = 14 (ed-on-bls12-377: 252 = 18 * 14) or 16 (254..256 bits).
 static int default_window(int curve, int form, size_t n) {
   int lg = ceil_log2_sz(n);
   if (form == MSM_FORM_AFFINE_GLV) return lg >= 25 ? 19 : (lg >= 14 ? 16 : (lg >= 7 ? 8 : 4));
-  if (curve == MSM_CURVE_ED_ON_BLS12_377) return lg >= 21 ? 18 : (lg >= 13 ? 14 : (lg >= 7 ? 9 : 4));
+  if (curve == MSM_CURVE_ED_ON_BLS12_377) return lg >= 13 ? 14 : (lg >= 7 ? 9 : 4);  // 252 = 18 * 14 = 28 * 9
   return lg >= 13 ? 16 : (lg >= 7 ? 8 : 4);
 }
 
@@ -343,8 +343,17 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
     LAUNCH(ctx, k_bucket_acc_v<C>, cdiv(V, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
            (const uint32_t*)ctx->po.p + NB, (const uint32_t*)ctx->pairkey[0].p, (const uint32_t*)ctx->ent.p,
            (const uint4*)ctx->bases.p, (uint32_t)V, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->elem[0].p);
+    // buckets with many pieces: halving passes; with few: a short serial loop in k_bucket_combine
+    const unsigned long long max_pieces = (ctx->h_totals[MAX_ROUNDS + 1] + BUCKET_SPLIT - 1) / BUCKET_SPLIT;
+    int serial_max = 1 << 30;
+    if (max_pieces > 16) {
+      serial_max = 0;  // every multi-piece bucket goes through the tree
+      for (int p = 0; (1ull << p) < max_pieces; p++)
+        LAUNCH(ctx, k_bucket_tree_pass<C>, cdiv(V, 128), 128, (const uint32_t*)ctx->po.p + NB,
+               (const uint32_t*)ctx->pairkey[0].p, (uint4*)ctx->elem[0].p, (uint32_t)V, (uint32_t)V, p);
+    }
     LAUNCH(ctx, k_bucket_combine<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p + NB,
-           (const uint4*)ctx->elem[0].p, (uint32_t)NB, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->buckets.p);
+           (const uint4*)ctx->elem[0].p, (uint32_t)NB, (uint32_t)BUCKET_SPLIT, serial_max, (uint4*)ctx->buckets.p);
   } else {
     LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
            (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);

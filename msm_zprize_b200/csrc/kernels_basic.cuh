@@ -111,13 +111,32 @@ __global__ void __launch_bounds__(128) k_bucket_acc_v(const uint32_t* __restrict
   C::st(vacc + (size_t)v * (C::ACC_FE * C::F::N / 4), acc);
 }
 
+// One halving pass over the virtual accumulators of every bucket (they are contiguous):
+// piece i of a bucket absorbs piece i + 2^p when i is a multiple of 2^(p+1).  After
+// ceil(log2(max pieces)) passes piece 0 holds the bucket sum -- used instead of the serial loop of
+// k_bucket_combine when a bucket has many pieces (heavily skewed scalars).
+template <class C>
+__global__ void __launch_bounds__(128) k_bucket_tree_pass(const uint32_t* __restrict__ voff, const uint32_t* __restrict__ vkey,
+                                                          uint4* __restrict__ vacc, uint32_t V, uint32_t Vtot, int p) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // candidate piece index v = t << (p + 1) is not bucket aligned,
+  if (t >= V) return;                                  // so every piece checks its own position
+  uint32_t b = vkey[t];
+  uint32_t i = t - voff[b];
+  if (i & ((2u << p) - 1u)) return;
+  uint32_t other = t + (1u << p);
+  if (other >= Vtot || vkey[other] != b) return;
+  constexpr int U4 = C::ACC_FE * C::F::N / 4;
+  C::st(vacc + (size_t)t * U4, C::add(C::ld(vacc + (size_t)t * U4), C::ld(vacc + (size_t)other * U4)));
+}
+
 template <class C>
 __global__ void __launch_bounds__(128) k_bucket_combine(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ voff,
                                                         const uint4* __restrict__ vacc, uint32_t NB, uint32_t split,
-                                                        uint4* __restrict__ buckets) {
+                                                        int serial_max, uint4* __restrict__ buckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= NB) return;
   uint32_t nv = (cnt[b] + split - 1) / split;
+  if (nv > (uint32_t)serial_max) nv = 1;  // already folded into piece 0 by the tree passes
   constexpr int U4 = C::ACC_FE * C::F::N / 4;
   typename C::Acc acc = C::zero();
   if (nv) acc = C::ld(vacc + (size_t)voff[b] * U4);
