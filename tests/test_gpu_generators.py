@@ -104,3 +104,22 @@ def test_full_size_against_cpu_port(mz, name, lg):
     prep = port.prepare_points(pts, n, threads)
     x, y, z, _ = port.msm(sc, prep, n, threads)
     assert (got.x, got.y, got.is_zero) == (x, y, z)
+
+
+@pytest.mark.parametrize("name", ["bls12-377", "pallas", "bls12-381", "ed-on-bls12-377"])
+@pytest.mark.parametrize("lg", [12, 14])
+def test_msm_test_ts_sizes_against_cpu_port(mz, name, lg):
+    """src/msm.test.ts:35-83,94-119: N up to 2^12 (and 2^14) on all four curves, msmUnsafe == oracle and
+    msmProjective == msmUnsafe -- here against the C++ port of the reference algorithm."""
+    from oracle.port import Port
+    n = 1 << lg
+    with mz.MsmEngine(name) as eng:
+        d_pts, d_sc, pts, sc = _gen(eng, mz, n, 100 + lg)
+        eng.set_bases_device(d_pts, n)
+        got = eng.run(d_sc, n, on_device=True)
+        proj = eng.run(d_sc, n, on_device=True, form=mz.FORM_PROJECTIVE) if name != "ed-on-bls12-377" else got
+    port = Port(name)
+    prep = port.prepare_points(pts, n, 4)
+    x, y, z, _ = port.msm(sc, prep, n, 4)
+    assert (got.x, got.y, got.is_zero) == (x, y, z)
+    assert (proj.x, proj.y) == (x, y)
