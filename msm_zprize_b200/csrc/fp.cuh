@@ -64,6 +64,10 @@ __device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) {
   asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
+// full 32x32 -> 64 product as ONE wide multiply (separate mul.lo / mul.hi stay two instructions)
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
 __device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) {
   uint32_t r;
   asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -119,6 +123,11 @@ inline uint32_t subc_cc(uint32_t a, uint32_t b) {
 inline uint32_t subc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a - b - msm_cf()); }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
 inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+  uint64_t t = (uint64_t)a * b;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+}
 inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
 inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
 inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
@@ -249,10 +258,8 @@ MSM_HD void mont_row(uint32_t* U, uint32_t* V, const uint32_t* a, uint32_t bi) {
   if (FIRST) {
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
-      V[j] = mul_lo(a[j], bi);
-      V[j + 1] = mul_hi(a[j], bi);
-      U[j] = mul_lo(a[j + 1], bi);
-      U[j + 1] = mul_hi(a[j + 1], bi);
+      mul_wide(a[j], bi, V[j], V[j + 1]);
+      mul_wide(a[j + 1], bi, U[j], U[j + 1]);
     }
     V[N] = 0;
   } else {
@@ -322,9 +329,141 @@ MSM_HD Fe<F> fe_mul(const Fe<F>& a, const Fe<F>& b) {
   return r;
 }
 
+// Out-of-line product for the latency-bound tail kernels (one warp or a few): their bodies are
+// dozens of inlined products otherwise (70-220 KB of SASS against a 32 KB instruction cache).
+#ifdef __CUDACC__
+template <class F>
+__device__ __noinline__ Fe<F> fe_mul_call(Fe<F> a, Fe<F> b) {
+  return fe_mul(a, b);
+}
+#else
+template <class F>
+inline Fe<F> fe_mul_call(const Fe<F>& a, const Fe<F>& b) {
+  return fe_mul(a, b);
+}
+#endif
+
+// One Montgomery reduction row on the split accumulator: mont_row with the a*b part removed.
+template <class F, bool FIRST>
+MSM_HD void redc_row(uint32_t* U, uint32_t* V) {
+  constexpr int N = F::N;
+  if (!FIRST) {
+    V[0] = add_cc(V[0], U[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j++) U[j] = addc_cc(U[j + 2], 0u);
+    U[N - 2] = addc_cc(U[N], 0u);
+    U[N - 1] = addc(0u, 0u);
+  }
+  V[N] = 0;
+  uint32_t m = mul_lo(V[0], F::M0v());
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      mul_wide(F::P(j + 1), m, U[j], U[j + 1]);
+    }
+  } else {
+    U[0] = mad_lo_cc(F::P(1), m, U[0]);
+    U[1] = madc_hi_cc(F::P(1), m, U[1]);
+#pragma unroll
+    for (int j = 2; j < N - 2; j += 2) {
+      U[j] = madc_lo_cc(F::P(j + 1), m, U[j]);
+      U[j + 1] = madc_hi_cc(F::P(j + 1), m, U[j + 1]);
+    }
+    if (N > 2) {
+      U[N - 2] = madc_lo_cc(F::P(N - 1), m, U[N - 2]);
+      U[N - 1] = madc_hi(F::P(N - 1), m, U[N - 1]);
+    }
+  }
+  V[0] = mad_lo_cc(F::P(0), m, V[0]);
+  V[1] = madc_hi_cc(F::P(0), m, V[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    V[j] = madc_lo_cc(F::P(j), m, V[j]);
+    V[j + 1] = madc_hi_cc(F::P(j), m, V[j + 1]);
+  }
+  V[N] = addc(V[N], 0u);
+}
+
+// a^2 / R.  The N(N-1)/2 cross products a_i*a_j (i<j) are accumulated once into two word-aligned
+// planes (E: i+j even, O: i+j odd, held one word up) so that every lo/hi pair still fuses into one
+// wide multiply-add; the sum is doubled, the N squares added, and the 2N-word result reduced with
+// N redc rows: N(N+1)/2 + N^2 wide products against 2N^2 for fe_mul.
+// Carry-outs of the per-row chains land in a word that so far holds at most another chain's carry
+// (row i ends one pair beyond row i-1 in each plane), so a plain addc is exact.
 template <class F>
 MSM_HD Fe<F> fe_sqr(const Fe<F>& a) {
-  return fe_mul(a, a);
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0, "even limb count");
+  uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) E[k] = O[k] = 0;
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    {  // j - i odd: word i+j is odd, O index i+j-1
+      int last = 0;
+#pragma unroll
+      for (int j = i + 1; j < N; j += 2) {
+        int k = i + j - 1;
+        O[k] = (j == i + 1) ? mad_lo_cc(a.v[i], a.v[j], O[k]) : madc_lo_cc(a.v[i], a.v[j], O[k]);
+        O[k + 1] = madc_hi_cc(a.v[i], a.v[j], O[k + 1]);
+        last = k + 1;
+      }
+      O[last + 1] = addc(O[last + 1], 0u);
+    }
+    if (i + 2 < N) {  // j - i even: E index i+j
+      int last = 0;
+#pragma unroll
+      for (int j = i + 2; j < N; j += 2) {
+        int k = i + j;
+        E[k] = (j == i + 2) ? mad_lo_cc(a.v[i], a.v[j], E[k]) : madc_lo_cc(a.v[i], a.v[j], E[k]);
+        E[k + 1] = madc_hi_cc(a.v[i], a.v[j], E[k + 1]);
+        last = k + 1;
+      }
+      E[last + 1] = addc(E[last + 1], 0u);
+    }
+  }
+  // C = E + (O one word up); word 0 is empty
+  uint32_t D[2 * N];
+  D[0] = 0;
+  D[1] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 2 * N - 1; k++) D[k] = addc_cc(E[k], O[k - 1]);
+  D[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+  // doubled, plus the squares
+#pragma unroll
+  for (int k = 2 * N - 1; k >= 1; k--) D[k] = (D[k] << 1) | (D[k - 1] >> 31);
+  D[0] = mad_lo_cc(a.v[0], a.v[0], D[0]);
+  D[1] = madc_hi_cc(a.v[0], a.v[0], D[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) {
+    D[2 * i] = madc_lo_cc(a.v[i], a.v[i], D[2 * i]);
+    D[2 * i + 1] = madc_hi_cc(a.v[i], a.v[i], D[2 * i + 1]);
+  }
+  D[2 * N - 2] = madc_lo_cc(a.v[N - 1], a.v[N - 1], D[2 * N - 2]);
+  D[2 * N - 1] = madc_hi(a.v[N - 1], a.v[N - 1], D[2 * N - 1]);
+  // reduce the low half, N rows
+  uint32_t A0[N + 1], A1[N + 1];
+  A0[N] = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) A1[k] = D[k];
+  redc_row<F, true>(A0, A1);  // X = A1, Y = A0
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    redc_row<F, false>(A1, A0);
+    if (i + 1 < N) redc_row<F, false>(A0, A1);
+  }
+  // X = A0, Y = A1:  (Y + (X >> 32)) <= p, plus the high half (< p)
+  Fe<F> r;
+  r.v[0] = add_cc(A1[0], A0[1]);
+#pragma unroll
+  for (int w = 1; w < N - 1; w++) r.v[w] = addc_cc(A1[w], A0[w + 1]);
+  r.v[N - 1] = addc(A1[N - 1], A0[N]);
+  r.v[0] = add_cc(r.v[0], D[N]);
+#pragma unroll
+  for (int w = 1; w < N - 1; w++) r.v[w] = addc_cc(r.v[w], D[N + w]);
+  r.v[N - 1] = addc(r.v[N - 1], D[2 * N - 1]);
+  fe_reduce_once(r);
+  return r;
 }
 
 // a * (small unsigned constant), by double-and-add on the constant's bits (c >= 1)

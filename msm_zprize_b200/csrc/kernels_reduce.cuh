@@ -31,7 +31,7 @@ __device__ __forceinline__ void quad_mul4(const Fe<F>& a0, const Fe<F>& b0, cons
     x.v[i] = q == 0 ? a0.v[i] : (q == 1 ? a1.v[i] : (q == 2 ? a2.v[i] : a3.v[i]));
     y.v[i] = q == 0 ? b0.v[i] : (q == 1 ? b1.v[i] : (q == 2 ? b2.v[i] : b3.v[i]));
   }
-  Fe<F> p = fe_mul(x, y);
+  Fe<F> p = fe_mul_call(x, y);
 #pragma unroll
   for (int i = 0; i < F::N; i++) {
     p0.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 0);

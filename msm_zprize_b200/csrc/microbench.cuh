@@ -88,4 +88,22 @@ __global__ void k_mb_modmul(uint32_t* out, int iters, uint32_t seed) {
   if (acc == 0x12345678u) out[0] = acc;
 }
 
+// dependent chain of Montgomery squarings per thread (two chains for ILP, like k_mb_modmul)
+template <class F>
+__global__ void k_mb_modsqr(uint32_t* out, int iters, uint32_t seed) {
+  Fe<F> x = fe_one<F>(), y = fe_one<F>();
+  x.v[0] ^= seed + threadIdx.x;
+  y.v[1] ^= seed * 5 + blockIdx.x + 7u * threadIdx.x;
+  fe_reduce_once(x);
+  fe_reduce_once(y);
+  for (int it = 0; it < iters; it++) {
+    x = fe_sqr(x);
+    y = fe_sqr(y);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < F::N; j++) acc ^= x.v[j] ^ y.v[j];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
 }  // namespace msm

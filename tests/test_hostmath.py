@@ -61,6 +61,29 @@ def fe_op(lib, field, op, a, b=0):
 
 
 @pytest.mark.parametrize("field", [0, 1, 2, 3])
+def test_field_sqr_carry_patterns(lib, field):
+    """fe_sqr has its own cross-product / doubling / redc carry chains (fp.cuh): words of all ones,
+    single set words and random values, against both the integers and fe_mul(a, a)."""
+    p, n = FIELDS[field]
+    Ri = pow(1 << RBITS[field], -1, p)
+    rng = random.Random(0x5A5A + field)
+    vals = []
+    for i in range(n):
+        vals.append((0xFFFFFFFF << (32 * i)) % p)
+        vals.append(((1 << (32 * (i + 1))) - 1) % p)
+        vals.append((p - 1) ^ (0xFFFFFFFF << (32 * i)) if ((p - 1) ^ (0xFFFFFFFF << (32 * i))) < p else p - 1 - i)
+    for _ in range(3000):
+        v = 0
+        for i in range(n):
+            v |= rng.choice([0, 0xFFFFFFFF, 0x80000000, 1, rng.getrandbits(32), rng.getrandbits(32)]) << (32 * i)
+        vals.append(v % p)
+    for a in vals:
+        got = fe_op(lib, field, 6, a)
+        assert got == a * a * Ri % p
+        assert got == fe_op(lib, field, 0, a, a)
+
+
+@pytest.mark.parametrize("field", [0, 1, 2, 3])
 def test_field_ops(lib, field):
     p, n = FIELDS[field]
     R = 1 << RBITS[field]

@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msm_zprize_b200.engine import microbench  # noqa: E402
 
 # (variants 0 / 1 of the library are not reported: ptxas rewrites their chains into mixed sequences)
-NAMES = {2: "imad_wide_carry", 5: "imad_hi", 8: "iadd", 3: "modmul_12limb", 4: "modmul_8limb"}
+NAMES = {2: "imad_wide_carry", 5: "imad_hi", 8: "iadd", 3: "modmul_12limb", 4: "modmul_8limb",
+         6: "modsqr_12limb", 7: "modsqr_8limb"}
 out = {}
 for which, name in NAMES.items():
     iters = 256
