@@ -318,10 +318,25 @@ def main():
     hot_modmul = (7 if te else 5)  # modmuls of one addition done inside the dominant kernel
     hot_lp = n_adds * hot_modmul * lp_mod
     achieved = hot_lp / (hot_ms * 1e-3) if hot_ms > 0 else 0.0
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/), when
+    # it was taken on this workload; a live run cannot measure it without a profiler
+    traffic, traffic_src = None, None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if rec["workload"] == workload_name(args.curve, args.log2n) and args.window == 0:
+            traffic = rec["dram_bytes_per_launch"]
+            traffic_src = "profiles/r01_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, mean of the " \
+                          "%d launches of one step)" % rec["launches"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "imad", "kernel": "k_bucket_acc" if te else "k_bwd (batched-affine backward pass)",
         "achieved": achieved / 1e12, "peak": peak_lp / 1e12, "unit": "T limb-products/s",
-        "frac": achieved / peak_lp if peak_lp else None, "traffic": None,
+        "frac": achieved / peak_lp if peak_lp else None, "traffic": traffic,
+        "traffic_source": traffic_src,
+        # bytes one addition has to move in this kernel: two points + the prefix product in, one point out, keys
+        # (twisted Edwards: one cached base point + its entry; the accumulator stays in registers)
+        "algorithmic_bytes": (n_adds / max(hot_launches, 1)) * ((3 * n32 * 4 + 4) if te else (7 * n32 * 4 + 16)),
         "peak_source": "live micro-benchmark: IMAD.WIDE.U32(.X) carry-chain issue rate on this GPU (msm_b200_microbench 2)",
         "algorithmic_work": f"{hot_modmul} of the {8 if te else 6} modmuls per point addition x {lp_mod} limb products x "
                             f"{n_adds // steps} additions per step",

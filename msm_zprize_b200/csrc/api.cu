@@ -1,4 +1,5 @@
 // libmsm_b200.so -- the C ABI (include/msm_b200.h) over the per-curve engines.
+#include <cstdlib>
 #include "engine.cuh"
 #include "microbench.cuh"
 
@@ -148,6 +149,9 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   ctx->device = device;
   ctx->curve = curve;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* e = getenv("MSM_B200_FINISH_ADD")) ctx->finish_add_modmuls = atof(e);
+  if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = atof(e);
+  if (const char* e = getenv("MSM_B200_FINISH_ELEMS")) ctx->finish_max_elems = atoi(e);
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {

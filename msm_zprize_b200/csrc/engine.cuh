@@ -36,6 +36,10 @@ struct msm_b200_ctx {
   std::string err;
   int launches = 0;
   int sm_count = 148;
+  // cost model of the tree tail (run_affine_glv); MSM_B200_FINISH_ADD / MSM_B200_FINISH_ROUND override (tuning)
+  double finish_add_modmuls = 18.0;
+  double finish_round_modmuls = 1.0e6;
+  int finish_max_elems = FINISH_MAX_ELEMS;
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
@@ -493,6 +497,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   RET_IF(ensure(ctx, ctx->fin, FinBuf<F>::bytes(NB)));
   std::vector<std::pair<int, int>> hot;
   int rounds_run = 0;
+  bool finished_projective = false;
   RET_IF(wait_for_bases(ctx));
   for (int r = 0; r < R; r++) {
     const size_t P = ctx->h_totals[r];
@@ -521,12 +526,21 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.M1 = 0;
     a.B0 = 0;
     a.blktot = nullptr;
-    // tail: one thread per unfinished bucket -- only when few pair slots AND few elements per bucket remain
-    if (P <= (size_t)FINISH_MAX && ((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)FINISH_MAX_ELEMS) {
+    // tail: one thread per bucket finishes the sums with projective mixed additions once that is cheaper
+    // than the rounds still to come.  Cost model in units of field products at full rate, fitted with
+    // tools/sweep_finish.sh: a round costs finish_round_modmuls (product tree, inversion, launch gaps) on
+    // top of 6 per addition; the tail costs finish_add_modmuls per addition (11 products, times the
+    // divergence of a thread-per-bucket loop).  Only with few elements per bucket (serial chain).
+    unsigned long long adds_left = 0;
+    for (int s = r; s < R; s++) adds_left += ctx->h_totals[MAX_ROUNDS + 3 + s];
+    if (((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)ctx->finish_max_elems &&
+        (double)adds_left * (ctx->finish_add_modmuls - 6.0) <= (double)(R - r) * ctx->finish_round_modmuls) {
+      RET_IF(ensure(ctx, ctx->buckets, NB * 3 * FE));
       if (r == 0)
-        LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB);
+        LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
       else
-        LAUNCH(ctx, (k_finish<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB);
+        LAUNCH(ctx, (k_finish<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+      finished_projective = true;
       break;
     }
     // pairs per thread: small rounds run as ONE full wave of resident blocks (no tail, few thread
@@ -588,7 +602,11 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   CK(cudaGetLastError());
   int e3 = T.mark();
   // --- bucket reduction
-  {
+  if (finished_projective) {
+    AccBucketLoader<WeierCurve<F, B3>> ld;
+    ld.buckets = (const uint4*)ctx->buckets.p;
+    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
+  } else {
     AffineBucketLoader<F, B3> ld;
     ld.fin = (const uint4*)ctx->fin.p;
     ld.cap = NB;

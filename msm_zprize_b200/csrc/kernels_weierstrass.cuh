@@ -30,8 +30,7 @@ constexpr int TOP_CTA_MAX = 512;   // the top block handles up to this many elem
 constexpr int TREE_MAX = 65536;   // serial levels until at most this many elements remain
 constexpr int MAX_ROUNDS = 30;
 constexpr int N_TOTALS = 2 * MAX_ROUNDS + 8;  // see k_scan
-constexpr int FINISH_MAX = 32768;
-constexpr int FINISH_MAX_ELEMS = 16;  // ... and at most this many elements per bucket  // finish the tree per bucket once at most this many pair slots are left
+constexpr int FINISH_MAX_ELEMS = 16;  // the tree tail (k_finish) runs only with at most this many elements per bucket
 
 // ------------------------------------------------------------------------------------------
 // ingest
@@ -562,27 +561,35 @@ __global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
   }
 }
 
-// Tail of the tree: when few pair slots are left, every unfinished bucket is summed by one thread
-// (projective mixed additions + its own inversion) instead of running more latency-bound rounds.
+// Tail of the tree.  Once the additions that are left cost less as projective mixed additions than
+// as further latency-bound rounds (each round pays a product tree + one inversion), every bucket is
+// summed by one thread and ALL bucket sums are written out projective (no inversion): unfinished
+// buckets from their remaining elements, finished ones from `fin`, empty ones as the neutral
+// element.  The bucket reduction then reads this array instead of `fin`.
 template <class F, uint32_t B3, bool R0>
-__global__ void __launch_bounds__(64) k_finish(RoundArgs<F> a, uint32_t NB) {
+__global__ void __launch_bounds__(64) k_finish(RoundArgs<F> a, uint32_t NB, uint4* __restrict__ buckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= NB) return;
-  uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
-  if (n < (R0 ? 1u : 2u)) return;
-  size_t e0 = 2 * (size_t)a.po_r[b];
-  Aff<F> A = R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0);
-  if (n == 1) {
-    a.fin.store(b, A);
-    return;
-  }
-  Proj<F> acc = proj_from_aff(A);
+  uint4* o = buckets + (size_t)b * (3 * F::N / 4);
+  const uint32_t cnt = a.cnt[b];
+  uint32_t n = (uint32_t)(((unsigned long long)cnt + (1ull << a.r) - 1) >> a.r);
+  Proj<F> acc;
+  if (cnt == 0) {
+    acc = proj_zero<F>();
+  } else if (!R0 && n == 1) {
+    acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
+  } else {
+    size_t e0 = 2 * (size_t)a.po_r[b];
+    acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0));
 #pragma unroll 1
-  for (uint32_t j = 1; j < n; j++) {
-    Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
-    if (!aff_is_inf(Q)) acc = proj_add_mixed<F, B3>(acc, Q);
+    for (uint32_t j = 1; j < n; j++) {
+      Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
+      if (!aff_is_inf(Q)) acc = proj_add_mixed<F, B3>(acc, Q);
+    }
   }
-  a.fin.store(b, proj_to_aff(acc));
+  st_aos<F>(o, acc.X);
+  st_aos<F>(o + F::N / 4, acc.Y);
+  st_aos<F>(o + 2 * F::N / 4, acc.Z);
 }
 
 // upper levels of the product tree: plain arrays of field elements
