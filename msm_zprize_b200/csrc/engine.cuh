@@ -40,6 +40,8 @@ struct msm_b200_ctx {
   double finish_add_modmuls = 18.0;
   double finish_round_modmuls = 1.0e6;
   int finish_max_elems = FINISH_MAX_ELEMS;
+  int reduce_gb0 = 3;          // MSM_B200_REDUCE_GB0 (tuning)
+  size_t reduce_warp_min = 4096;  // MSM_B200_REDUCE_WARP_MIN: levels with more items use one lane per item
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
@@ -258,7 +260,10 @@ template <class C, class Loader>
 static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K, int c) {
   constexpr size_t ITEM = (size_t)item_u4<C>() * 16;
   int remaining = c - 1;
-  int gb = remaining < 3 ? remaining : 3;  // level 0: 8 buckets per thread
+  // level 0: 8 buckets per thread (measured best of 4 / 8 / 16 / 32 at 2^18 buckets: 1.59 / 1.28 / 1.44 / 1.94 ms
+  // for the whole reduction)
+  int gb0 = ctx->reduce_gb0;
+  int gb = remaining < gb0 ? remaining : gb0;
   size_t items = NB >> gb;
   RET_IF(ensure(ctx, ctx->red[0], items * ITEM));
   RET_IF(ensure(ctx, ctx->red[1], (items / 2 + 1) * ITEM));
@@ -266,7 +271,7 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   remaining -= gb;
   int cur = 0;
   while (remaining > 0) {
-    if (items > 4096) {
+    if (items > ctx->reduce_warp_min) {
       gb = remaining < 5 ? remaining : 5;  // throughput-bound level: one item per lane, groups of 2^gb lanes
       LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
              (uint4*)ctx->red[cur ^ 1].p);
