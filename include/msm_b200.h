@@ -170,8 +170,10 @@ int msm_b200_test_digits(msm_b200_ctx* ctx, const void* scalars_host, size_t n, 
 /* Integer-pipe micro-benchmarks (the measured roofline denominators): which = 0 IMAD (mad.lo),
  * 1 IMAD.WIDE (mad.wide.u32), 2 IMAD.WIDE with carry in/out (mad.lo.cc/madc.hi.cc chains),
  * 5 IMAD.HI, 8 IADD3, 3 Montgomery product 12 limbs, 4 Montgomery product 8 limbs,
- * 6 / 7 Montgomery squaring 12 / 8 limbs.
- * Returns operations per second (limb products for 0-2 and 5, adds for 8, modmuls for 3-4, 6-7). */
+ * 6 / 7 Montgomery squaring 12 / 8 limbs; 9 / 10 / 11 latency of a chain of projective doublings in ONE warp
+ * (quad-cooperative 12 limbs / one lane 12 limbs / quad-cooperative 8 limbs: what bounds the Horner tail).
+ * Returns operations per second (limb products for 0-2 and 5, adds for 8, modmuls for 3-4 and 6-7,
+ * doublings for 9-11). */
 int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, float* ms);
 
 #ifdef __cplusplus

@@ -399,6 +399,9 @@ int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, f
       case 4: k_mb_modmul<PallasFp><<<blocks, threads>>>(d, iters, 12345u); break;
       case 6: k_mb_modsqr<Bls377Fq><<<blocks, threads>>>(d, iters, 12345u); break;
       case 7: k_mb_modsqr<PallasFp><<<blocks, threads>>>(d, iters, 12345u); break;
+      case 9: k_mb_dbl_chain<WeierCurve<Bls377Fq, 3>, true><<<1, 32>>>(d, iters, 12345u); break;
+      case 10: k_mb_dbl_chain<WeierCurve<Bls377Fq, 3>, false><<<1, 32>>>(d, iters, 12345u); break;
+      case 11: k_mb_dbl_chain<WeierCurve<PallasFp, 15>, true><<<1, 32>>>(d, iters, 12345u); break;
       default: cudaFree(d); return fail(nullptr, MSM_E_INVALID, "unknown benchmark");
     }
     CK(cudaEventRecord(e1));
@@ -407,7 +410,9 @@ int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, f
   }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
-  if (which == 3 || which == 4 || which == 6 || which == 7)
+  if (which >= 9)
+    ops = (double)iters;  // doublings of the one chain
+  else if (which == 3 || which == 4 || which == 6 || which == 7)
     ops = (double)blocks * threads * iters * 2.0;
   else
     ops = (double)blocks * threads * iters * (double)MB_INNER * MB_CHAINS;

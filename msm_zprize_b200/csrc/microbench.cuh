@@ -6,6 +6,7 @@
 // each variant is checked in profiles/ (one IMAD / IMAD.WIDE / IMAD.HI / IADD3 per counted op).
 #pragma once
 #include "kernels_common.cuh"
+#include "kernels_reduce.cuh"
 
 namespace msm {
 
@@ -104,6 +105,21 @@ __global__ void k_mb_modsqr(uint32_t* out, int iters, uint32_t seed) {
 #pragma unroll
   for (int j = 0; j < F::N; j++) acc ^= x.v[j] ^ y.v[j];
   if (acc == 0x12345678u) out[0] = acc;
+}
+
+// latency of the one-warp tail: a chain of point doublings, quad-cooperative (QUAD) or one lane alone
+template <class C, bool QUAD>
+__global__ void __launch_bounds__(32) k_mb_dbl_chain(uint32_t* out, int iters, uint32_t seed) {
+  typename C::Acc acc = C::zero();
+  acc.X.v[0] = seed & 0xffffu;
+  acc.Y.v[1] = 5u;
+  acc.Z.v[0] = 1u;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) acc = QUAD ? C::dbl_quad(acc) : C::dbl(acc);
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < C::F::N; j++) x ^= acc.X.v[j] ^ acc.Y.v[j] ^ acc.Z.v[j];
+  if (x == 0x12345678u) out[0] = x;
 }
 
 }  // namespace msm

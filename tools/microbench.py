@@ -9,7 +9,8 @@ from msm_zprize_b200.engine import microbench  # noqa: E402
 
 # (variants 0 / 1 of the library are not reported: ptxas rewrites their chains into mixed sequences)
 NAMES = {2: "imad_wide_carry", 5: "imad_hi", 8: "iadd", 3: "modmul_12limb", 4: "modmul_8limb",
-         6: "modsqr_12limb", 7: "modsqr_8limb"}
+         6: "modsqr_12limb", 7: "modsqr_8limb", 9: "dbl_chain_quad_12limb", 10: "dbl_chain_lone_12limb",
+         11: "dbl_chain_quad_8limb"}
 out = {}
 for which, name in NAMES.items():
     iters = 256
