@@ -41,6 +41,7 @@ struct msm_b200_ctx {
   double finish_round_modmuls = 1.0e6;
   int finish_max_elems = FINISH_MAX_ELEMS;
   int reduce_gb0 = 3;          // MSM_B200_REDUCE_GB0 (tuning)
+  int reduce_warp_gb = 3;         // MSM_B200_REDUCE_WARP_GB (2^18 buckets: 5 -> 1.29 ms, 4 -> 1.25, 3 -> 1.22, 2 -> 1.24)
   size_t reduce_warp_min = 4096;  // MSM_B200_REDUCE_WARP_MIN: levels with more items use one lane per item
   // resident bases
   DevBuf bases;
@@ -272,7 +273,7 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   int cur = 0;
   while (remaining > 0) {
     if (items > ctx->reduce_warp_min) {
-      gb = remaining < 5 ? remaining : 5;  // throughput-bound level: one item per lane, groups of 2^gb lanes
+      gb = remaining < ctx->reduce_warp_gb ? remaining : ctx->reduce_warp_gb;  // one item per lane, groups of 2^gb lanes
       LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
              (uint4*)ctx->red[cur ^ 1].p);
     } else {
