@@ -30,7 +30,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "bls12_377_g1_msm_throughput"
+METRIC = "bls12_377_g1_msm_throughput"  # BASELINE.json's metric; other curves: <curve>_msm_throughput
+
+
+def metric_name(curve):
+    return METRIC if curve == "bls12-377" else curve.replace("-", "_") + "_msm_throughput"
+
+
+# stdout carries exactly ONE line, the JSON result: libraries that print banners to fd 1 (NCCL's version line)
+# are sent to stderr for the lifetime of the process
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
 UNIT = "Mpoints/s"
 CURVES = {"bls12-377": (48, 12, 126), "pallas": (32, 8, 127), "ed-on-bls12-377": (32, 8, 251)}
 
@@ -160,8 +174,8 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     value = n / (ms * 1e-3) / 1e6
     sample = f"2^{int(math.log2(n))} points per step (bounded sample of the 2^{args.log2n} workload), c={port.default_window(n)}"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    emit(({
+        "impl": "reference", "metric": metric_name(args.curve), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args.curve, args.log2n),
@@ -363,7 +377,7 @@ def main():
                "ms": sec * 1e3}
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "metric": metric_name(curve), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(curve, args.log2n), "window_bits": c_used, "n_windows": K_used,
@@ -382,7 +396,7 @@ def main():
                                 ("digits_ms", "sort_ms", "accumulate_ms", "hot_kernel_ms", "reduce_ms")},
         "wall_s_timed_region": wall_total,
     }
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
