@@ -126,6 +126,7 @@ __global__ void k_test_field(int op, const uint32_t* a, const uint32_t* b, uint3
   if (op == 0) r = fe_mul(x, y);
   else if (op == 1) r = fe_add(x, y);
   else if (op == 2) r = fe_sub(x, y);
+  else if (op == 4) r = fe_sqr(x);
   else r = fe_inv(x);
   for (int j = 0; j < F::N; j++) out[i * F::N + j] = r.v[j];
 }
@@ -328,7 +329,7 @@ int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t
 int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host, const uint32_t* b_host,
                            uint32_t* out_host, size_t n) {
   msm_b200_ctx* ctx = nullptr;
-  if (field < 0 || field > 3 || op < 0 || op > 3 || !a_host || !b_host || !out_host)
+  if (field < 0 || field > 3 || op < 0 || op > 4 || !a_host || !b_host || !out_host)
     return fail(nullptr, MSM_E_INVALID, "bad arguments");
   CK(cudaSetDevice(device));
   int N = (field == 0 || field == 3) ? 12 : 8;

@@ -46,6 +46,17 @@ def test_field_ops_on_device(mz, field):
     assert _vals(test_field_op(0, field, 0, A, B)) == [x * y * Ri % p for x, y in zip(a, b)]
     assert _vals(test_field_op(0, field, 1, A, B)) == [(x + y) % p for x, y in zip(a, b)]
     assert _vals(test_field_op(0, field, 2, A, B)) == [(x - y) % p for x, y in zip(a, b)]
+    # the squaring has its own carry chains (fp.cuh fe_sqr): words of all ones / single set words as well
+    sq = list(a)
+    for i in range(n):
+        sq += [(0xFFFFFFFF << (32 * i)) % p, ((1 << (32 * (i + 1))) - 1) % p, (1 << (32 * i)) % p]
+    for _ in range(400):
+        v = 0
+        for i in range(n):
+            v |= rng.choice([0, 0xFFFFFFFF, 0x80000000, 1, rng.getrandbits(32)]) << (32 * i)
+        sq.append(v % p)
+    SQ = _limbs(sq, n)
+    assert _vals(test_field_op(0, field, 4, SQ, SQ)) == [x * x * Ri % p for x in sq]
     nz = [x if x else 1 for x in a][:64]
     assert _vals(test_field_op(0, field, 3, _limbs(nz, n), _limbs(nz, n))) == [pow(x, -1, p) * R * R % p for x in nz]
 
