@@ -56,3 +56,28 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and f != "hosttest.cpp":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|bigint_oracle|libmsm_port|oracle/", txt, flags=re.M), f
+
+
+def test_napi_addon_compiles():
+    """napi/msm_b200_addon.c (the Node binding of INTEGRATION.md) must stay in step with include/msm_b200.h:
+    syntax + type check against the header and a declaration-only stub of node_api.h (Node is not in this image)."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "napi", "stub"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "napi", "msm_b200_addon.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_ts_shim_uses_the_header_constants():
+    """ts/msm-b200.ts repeats the enum values of include/msm_b200.h; keep them equal."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "msm_b200.h")).read()
+    ts = open(os.path.join(ROOT, "ts", "msm-b200.ts")).read()
+    for c_name, ts_name in [("MSM_CURVE_BLS12_377_G1", "CURVE_BLS12_377_G1"), ("MSM_CURVE_PALLAS", "CURVE_PALLAS"),
+                            ("MSM_CURVE_ED_ON_BLS12_377", "CURVE_ED_ON_BLS12_377"),
+                            ("MSM_CURVE_BLS12_381_G1", "CURVE_BLS12_381_G1"), ("MSM_FORM_AFFINE_GLV", "FORM_AFFINE_GLV"),
+                            ("MSM_FORM_PROJECTIVE", "FORM_PROJECTIVE"), ("MSM_FORM_TE_EXTENDED", "FORM_TE_EXTENDED"),
+                            ("MSM_LAYOUT_LIMB29_MONT", "LAYOUT_LIMB29_MONT"), ("MSM_LAYOUT_LE_BYTES", "LAYOUT_LE_BYTES")]:
+        c_val = re.search(r"\b%s\s*=\s*(-?\d+)" % c_name, hdr).group(1)
+        ts_val = re.search(r"\b%s\s*=\s*(-?\d+)" % ts_name, ts).group(1)
+        assert c_val == ts_val, (c_name, c_val, ts_val)

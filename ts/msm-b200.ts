@@ -1,0 +1,103 @@
+/**
+ * TypeScript side of the B200 backend for mitschabaude/msm-zprize: the same three async functions that
+ * `createMsm()` (src/msm-batched-affine.ts:573-587), `msmProjective` (src/parallel.ts:69-87) and
+ * `createMsmBasic()` (src/msm-basic.ts:34-43) return, over the N-API addon (napi/msm_b200_addon.c) and
+ * thus over the C ABI of libmsm_b200.so (include/msm_b200.h).
+ *
+ * Wiring (the only change inside the reference): in `Weierstraß.create` / `TwistedEdwards.create`
+ * (src/parallel.ts:65,199) pick these functions when `process.env.MSM_BACKEND === "b200"`:
+ *
+ *     const { msm, msmUnsafe } = process.env.MSM_BACKEND === "b200"
+ *       ? createMsmB200(Inputs, CURVE_BLS12_377_G1) : createMsm(Inputs);
+ *
+ * The drivers (scripts/run-msm-377.ts, run-msm-pallas.ts, run-msm-ed-377.ts, scripts/msm-*.ts) stay as they are:
+ * they still pass pointers into the curve's wasm memories and get back `{ result, log }` with `result` a
+ * pointer to a projective (Weierstraß) or extended (twisted Edwards) point in Montgomery form, which they
+ * normalise themselves (scripts/msm-weierstrass.ts:90-92, scripts/msm-twisted-edwards.ts:87).
+ *
+ * Not compiled or run in this repository's image (no Node); the tested mirror of this file is
+ * msm_zprize_b200/parallel.py.
+ */
+// @ts-ignore -- built by node-gyp from napi/binding.gyp
+import addon from "../napi/build/Release/msm_b200.node";
+
+// include/msm_b200.h
+export const CURVE_BLS12_377_G1 = 0, CURVE_PALLAS = 1, CURVE_ED_ON_BLS12_377 = 2, CURVE_BLS12_381_G1 = 3;
+export const FORM_AFFINE_GLV = 0, FORM_PROJECTIVE = 1, FORM_TE_EXTENDED = 2;
+export const LAYOUT_LIMB29_MONT = 0, LAYOUT_LE_BYTES = 1;
+
+type Timing = Record<string, number>;
+type AddonResult = { x: Uint8Array; y: Uint8Array; isZero: boolean; timing: Timing };
+
+function bytesToBigint(bytes: Uint8Array): bigint {
+  let x = 0n;
+  for (let i = bytes.length - 1; i >= 0; i--) x = (x << 8n) | BigInt(bytes[i]);
+  return x;
+}
+
+function toLog(timing: Timing, verbose: boolean): any[][] {
+  // same shape as createLog's rows (src/msm-common.ts:192-230): ["phase... 1.23ms"]
+  if (!verbose) return [];
+  return Object.entries(timing)
+    .filter(([k]) => k !== "windowBits" && k !== "windows" && k !== "rounds")
+    .map(([k, v]) => [`${k}... ${v.toFixed(2)}ms`]);
+}
+
+/** Resident-bases bookkeeping shared by the three entry points: the benchmark drivers reuse `pointPtr`
+ *  over many runs with fresh scalars (scripts/msm-weierstrass.ts:19,29-33). */
+function makeRunner(ctx: unknown, Field: any, Scalar: any) {
+  let basesPtr = -1, basesN = 0;
+  return async function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number) {
+    if (pointPtr !== basesPtr || N > basesN) {
+      addon.setBases(ctx, Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
+      basesPtr = pointPtr;
+      basesN = N;
+    }
+    return (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
+  };
+}
+
+/** Weierstraß curves: drop-in for `createMsm(Inputs)` plus `msmProjective`. */
+export function createMsmB200(Inputs: any, curveId: number, device = 0) {
+  const { Field, Scalar, Affine, Projective } = Inputs;
+  const ctx = addon.createContext(curveId, device);
+  const run = makeRunner(ctx, Field, Scalar);
+
+  async function call(scalarPtr: number, pointPtr: number, N: number, verbose: boolean, form: number, c: number) {
+    // allocated before the scope so it survives it, like the reference's `result` (src/msm-batched-affine.ts:87-90)
+    const result = Field.global.getPointer(Projective.size);
+    const r = await run(scalarPtr, pointPtr, N, form, c);
+    using _ = Field.local.atCurrentOffset;
+    const affine = Field.local.getPointer(Affine.size);
+    // canonical (x, y) -> Montgomery affine point -> projective with Z = mg1 (src/curve-affine.ts:273-284,
+    // src/curve-projective.ts:322-333); the zero point only carries the flag
+    Affine.writeBigint(affine, { x: bytesToBigint(r.x), y: bytesToBigint(r.y), isZero: r.isZero });
+    Projective.fromAffine(result, affine);
+    return { result, log: toLog(r.timing, verbose) };
+  }
+
+  const msm = (scalarPtr: number, pointPtr: number, N: number, verbose = false, { c = 0 }: { c?: number } = {}) =>
+    call(scalarPtr, pointPtr, N, verbose, FORM_AFFINE_GLV, c);
+  const msmProjective = (scalarPtr: number, pointPtr: number, N: number, { c = 0 }: { c?: number } = {}) =>
+    call(scalarPtr, pointPtr, N, false, FORM_PROJECTIVE, c);
+  // the engine always applies the safe addition rules (batchAddNew, src/curve-affine.ts:376-458), which agree
+  // with the unsafe ones wherever those are defined
+  return { msm, msmUnsafe: msm, msmProjective, destroy: () => addon.destroy(ctx) };
+}
+
+/** Twisted Edwards (ed-on-bls12-377): drop-in for `createMsmBasic(Inputs)` (src/msm-basic.ts:34-43). */
+export function createMsmBasicB200(Inputs: any, device = 0) {
+  const { Field, Scalar, Curve } = Inputs;
+  const ctx = addon.createContext(CURVE_ED_ON_BLS12_377, device);
+  const run = makeRunner(ctx, Field, Scalar);
+
+  async function msm(scalarPtr: number, pointPtr: number, N: number, { c = 0 }: { c?: number } = {}) {
+    const result = Field.global.getPointer(Curve.size);
+    const r = await run(scalarPtr, pointPtr, N, FORM_TE_EXTENDED, c);
+    const x = bytesToBigint(r.x), y = bytesToBigint(r.y);
+    // extended coordinates of the affine result: (x, y, 1, x*y)  (src/curve-twisted-edwards.ts:435-447)
+    Curve.fromBigint(result, { X: x, Y: y, Z: 1n, T: (x * y) % Field.p });
+    return { result, log: [] as any[][] };
+  }
+  return Object.assign(msm, { destroy: () => addon.destroy(ctx) });
+}
