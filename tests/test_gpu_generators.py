@@ -87,6 +87,38 @@ def test_large_n_properties(mz, name, lg):
         assert (a.x, a.y, a.is_zero) == (c.x, c.y, c.is_zero)
 
 
+@pytest.mark.parametrize("name,lg,c2", [("pallas", 20, 13), ("ed-on-bls12-377", 22, 16), ("bls12-377", 20, 14),
+                                        ("bls12-377", 22, 18), ("bls12-377", 24, 19)])
+def test_baseline_config_sizes_properties(mz, name, lg, c2):
+    """BASELINE.json configs[2..4] at their full sizes (Pallas 2^20, ed-on-bls12-377 2^22, BLS12-377 2^20..2^24),
+    where no CPU checker finishes in seconds: size-independent properties of the exact result --
+    a different window size gives the same point, and the sum over two unequal ranges (run_partial + combine,
+    the multi-GPU path) equals the whole."""
+    n = 1 << lg
+    with mz.MsmEngine(name) as eng:
+        pb = eng.point_bytes(mz.LAYOUT_LE_BYTES)
+        d_pts = eng.dev_alloc(n * pb)
+        d_sc = eng.dev_alloc(n * 32)
+        eng.random_points_device(d_pts, n, 0xB200 + lg)
+        eng.random_scalars_device(d_sc, n, 0x5CA1A + lg)
+        eng.set_bases_device(d_pts, n)
+        a = eng.run(d_sc, n, on_device=True)
+        b = eng.run(d_sc, n, on_device=True, window_bits=c2)
+        assert not a.is_zero
+        assert (a.x, a.y, a.is_zero) == (b.x, b.y, b.is_zero)
+        h = (n // 3) | 1
+        pbytes = eng.partial_bytes()
+        d_part = eng.dev_alloc(2 * pbytes)
+        eng.run_partial(d_sc, h, d_part, on_device=True)
+        eng.set_bases_device(d_pts + h * pb, n - h)
+        eng.run_partial(d_sc + h * 32, n - h, d_part + pbytes, on_device=True)
+        c = eng.combine(d_part, 2)
+        assert (a.x, a.y, a.is_zero) == (c.x, c.y, c.is_zero)
+        eng.dev_free(d_part)
+        eng.dev_free(d_sc)
+        eng.dev_free(d_pts)
+
+
 @pytest.mark.parametrize("name,lg", [("bls12-377", 18), ("pallas", 18)])
 def test_full_size_against_cpu_port(mz, name, lg):
     """BASELINE.json configs[1] size (BLS12-377 G1, n = 2^18): the GPU result must be bit-identical to the
