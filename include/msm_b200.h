@@ -135,6 +135,11 @@ int msm_b200_run_partial(msm_b200_ctx* ctx, const void* scalars, size_t n, int s
                          int on_device, int form, int window_bits, void* partial_dev,
                          msm_b200_timing* timing);
 size_t msm_b200_partial_bytes(const msm_b200_ctx* ctx);
+/* With timing == NULL, msm_b200_run_partial returns WITHOUT synchronising: the partial is ready in stream
+ * order on the context's stream, so a collective queued on that stream can follow at once.  The phase
+ * timings of that last call (the `log` of createLog, src/msm-common.ts:192-230) can be fetched afterwards
+ * with this function, which waits for the stream first. */
+int msm_b200_last_timing(msm_b200_ctx* ctx, msm_b200_timing* timing);
 /* Adds `count` gathered partials (device memory) and normalises: the "partition sum / final sum"
  * of src/msm-batched-affine.ts:299-322 across GPUs. */
 int msm_b200_combine(msm_b200_ctx* ctx, const void* partials_dev, int count, msm_b200_point* out);

@@ -94,8 +94,10 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
     rc = ops_of(ctx->curve)->run(ctx, d_s, n, layout, form, c, tm, digits_dump_dev);
   RET_IF(rc);
   RET_IF(wait_for_bases(ctx));  // (no-op unless the MSM never touched the bases, e.g. all-zero scalars)
+  ctx->pending.h2d[0] = t0;
+  ctx->pending.h2d[1] = t1;
   if (tm) {
-    tm->h2d_ms = T.ms(t0, t1);
+    if (ctx->pending.valid) tm->h2d_ms = T.ms(t0, t1);
     tm->kernel_launches = ctx->launches;
   }
   return 0;
@@ -214,13 +216,24 @@ int msm_b200_run_partial(msm_b200_ctx* ctx, const void* scalars, size_t n, int s
                          int window_bits, void* partial_dev, msm_b200_timing* timing) {
   if (!partial_dev) return fail(ctx, MSM_E_INVALID, "null partial pointer");
   auto w0 = std::chrono::steady_clock::now();
-  if (ctx) ctx->launches = 0;
+  if (ctx) {
+    ctx->launches = 0;
+    ctx->ev_used = 0;
+  }
   RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, timing));
   CK(cudaMemcpyAsync(partial_dev, ctx->partial.p, partial_bytes(ctx->curve), cudaMemcpyDeviceToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (timing)
+  if (timing) {  // without a timing struct the partial is ready in stream order; see msm_b200_last_timing
+    CK(cudaStreamSynchronize(ctx->stream));
     timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  }
   return 0;
+}
+
+int msm_b200_last_timing(msm_b200_ctx* ctx, msm_b200_timing* timing) {
+  if (!ctx || !timing) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  memset(timing, 0, sizeof *timing);
+  return resolve_timing(ctx, timing);
 }
 
 size_t msm_b200_partial_bytes(const msm_b200_ctx* ctx) { return ctx ? partial_bytes(ctx->curve) : 0; }
@@ -233,7 +246,10 @@ int msm_b200_run(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_la
                  int window_bits, msm_b200_point* out, msm_b200_timing* timing) {
   if (!out) return fail(ctx, MSM_E_INVALID, "null out pointer");
   auto w0 = std::chrono::steady_clock::now();
-  if (ctx) ctx->launches = 0;
+  if (ctx) {
+    ctx->launches = 0;
+    ctx->ev_used = 0;
+  }
   RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, timing));
   Timer T(ctx);
   int d0 = T.mark();
@@ -251,18 +267,19 @@ int msm_b200_run(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_la
 int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, const void* points, int point_layout,
                  size_t n, int form, int window_bits, msm_b200_point* out, msm_b200_timing* timing) {
   if (!out) return fail(ctx, MSM_E_INVALID, "null out pointer");
+  if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
   auto w0 = std::chrono::steady_clock::now();
-  if (ctx) ctx->launches = 0;
-  Timer T(ctx ? ctx : nullptr);
-  int i0 = ctx ? T.mark() : 0;
+  ctx->launches = 0;
+  ctx->ev_used = 0;
+  Timer T(ctx);
+  int i0 = T.mark();
   RET_IF(set_bases_impl(ctx, points, n, point_layout, 0, /*overlapped=*/true));
   int i1 = T.mark();
-  int launches0 = ctx->launches;
   RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, timing));
   RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
   if (timing) {
     timing->ingest_ms = T.ms(i0, i1);
-    timing->kernel_launches = ctx->launches + launches0;
+    timing->kernel_launches = ctx->launches;
     timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
   }
   return 0;

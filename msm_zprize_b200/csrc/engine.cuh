@@ -23,6 +23,18 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// Phase marks of the last MSM, resolved into a msm_b200_timing after the stream has drained: at once when the
+// caller passed a timing struct, or later through msm_b200_last_timing() so that the call itself need not
+// synchronise (the multi-GPU driver queues its collective behind the MSM first).
+struct PendingTiming {
+  bool valid = false;
+  int e[5] = {0, 0, 0, 0, 0};  // digits | sort | accumulate | reduce boundaries
+  std::vector<std::pair<int, int>> hot;
+  int window_bits = 0, n_windows = 0, rounds = 0;
+  unsigned long long n_adds = 0;
+  int h2d[2] = {-1, -1};  // scalar upload, set by the entry point
+};
+
 struct msm_b200_ctx {
   int device = 0;
   int curve = 0;
@@ -52,6 +64,8 @@ struct msm_b200_ctx {
   unsigned long long* h_totals = nullptr;  // pinned
   uint32_t* h_result = nullptr;            // pinned
   std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  PendingTiming pending;
 };
 
 #define CK(call)                                                                             \
@@ -127,26 +141,48 @@ static int ceil_log2_sz(size_t n) {
   return k;
 }
 
+// CUDA-event stopwatch.  All Timer objects of one call share the context's event pool and its cursor
+// (`ctx->ev_used`, reset by the C-ABI entry point), so marks taken at different levels never alias.
 struct Timer {
   msm_b200_ctx* ctx;
-  std::vector<cudaEvent_t>& ev;
-  size_t used = 0;
-  explicit Timer(msm_b200_ctx* c) : ctx(c), ev(c->ev) {}
-  int mark() {  // records an event, returns its index
-    if (used == ev.size()) {
+  explicit Timer(msm_b200_ctx* c) : ctx(c) {}
+  int mark() {  // records an event on the context's stream, returns its index
+    std::vector<cudaEvent_t>& ev = ctx->ev;
+    if (ctx->ev_used == ev.size()) {
       cudaEvent_t e;
       cudaEventCreate(&e);
       ev.push_back(e);
     }
-    cudaEventRecord(ev[used], ctx->stream);
-    return (int)used++;
+    cudaEventRecord(ev[ctx->ev_used], ctx->stream);
+    return (int)ctx->ev_used++;
   }
   float ms(int a, int b) {
     float t = 0;
-    cudaEventElapsedTime(&t, ev[a], ev[b]);
+    cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
     return t;
   }
 };
+
+static int resolve_timing(msm_b200_ctx* ctx, msm_b200_timing* tm) {
+  const PendingTiming& pt = ctx->pending;
+  if (!pt.valid) return 0;  // nothing was launched (empty input, all-zero scalars, digit dump)
+  CK(cudaStreamSynchronize(ctx->stream));
+  Timer T(ctx);
+  tm->digits_ms = T.ms(pt.e[0], pt.e[1]);
+  tm->sort_ms = T.ms(pt.e[1], pt.e[2]);
+  tm->accumulate_ms = T.ms(pt.e[2], pt.e[3]);
+  tm->reduce_ms = T.ms(pt.e[3], pt.e[4]);
+  tm->hot_kernel_ms = 0;
+  for (const auto& h : pt.hot) tm->hot_kernel_ms += T.ms(h.first, h.second);
+  tm->hot_kernel_launches = (int)pt.hot.size();
+  tm->window_bits = pt.window_bits;
+  tm->n_windows = pt.n_windows;
+  tm->rounds = pt.rounds;
+  tm->n_adds = pt.n_adds;
+  if (pt.h2d[0] >= 0) tm->h2d_ms = T.ms(pt.h2d[0], pt.h2d[1]);
+  tm->kernel_launches = ctx->launches;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // curve dispatch helpers
@@ -301,6 +337,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   using F = typename C::F;
   constexpr size_t FE = F::N * 4;
   Timer T(ctx);
+  ctx->pending.valid = false;
   const int b = S::QBITS;  // Scalar.sizeInBits, src/msm-basic.ts:55
   const int K = (b + 1 + c - 1) / c;
   const uint32_t L = 1u << (c - 1);
@@ -375,19 +412,17 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   ld.buckets = (const uint4*)ctx->buckets.p;
   RET_IF((reduce_buckets<C>(ctx, ld, NB, K, c)));
   int e4 = T.mark();
-  if (tm) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    tm->digits_ms = T.ms(e0, e1);
-    tm->sort_ms = T.ms(e1, e2);
-    tm->accumulate_ms = T.ms(e2, e3);
-    tm->reduce_ms = T.ms(e3, e4);
-    tm->hot_kernel_ms = T.ms(h0, h1);
-    tm->hot_kernel_launches = 1;
-    tm->window_bits = c;
-    tm->n_windows = K;
-    tm->rounds = 0;
-    tm->n_adds = ctx->h_totals[MAX_ROUNDS + 2];  // one mixed addition per sorted entry
+  {
+    PendingTiming& pt = ctx->pending;
+    pt.valid = true;
+    pt.e[0] = e0, pt.e[1] = e1, pt.e[2] = e2, pt.e[3] = e3, pt.e[4] = e4;
+    pt.hot.assign(1, std::make_pair(h0, h1));
+    pt.window_bits = c;
+    pt.n_windows = K;
+    pt.rounds = 0;
+    pt.n_adds = ctx->h_totals[MAX_ROUNDS + 2];  // one mixed addition per sorted entry
   }
+  if (tm) RET_IF(resolve_timing(ctx, tm));
   return 0;
 }
 
@@ -428,6 +463,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
                           msm_b200_timing* tm, uint32_t* digits_dump_dev) {
   constexpr size_t FE = F::N * 4;
   Timer T(ctx);
+  ctx->pending.valid = false;
   const int b = G::MAXBITS;  // Scalar.maxBits, src/wasm/glv.ts:216-226
   const int K = (b + 1 + c - 1) / c;
   const uint32_t L = 1u << (c - 1);
@@ -620,20 +656,17 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
   }
   int e4 = T.mark();
-  if (tm) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    tm->digits_ms = T.ms(e0, e1);
-    tm->sort_ms = T.ms(e1, e2);
-    tm->accumulate_ms = T.ms(e2, e3);
-    tm->reduce_ms = T.ms(e3, e4);
-    tm->hot_kernel_ms = 0;
-    for (auto& h : hot) tm->hot_kernel_ms += T.ms(h.first, h.second);
-    tm->hot_kernel_launches = (int)hot.size();
-    tm->window_bits = c;
-    tm->n_windows = K;
-    tm->rounds = rounds_run;
-    tm->n_adds = n_adds;
+  {
+    PendingTiming& pt = ctx->pending;
+    pt.valid = true;
+    pt.e[0] = e0, pt.e[1] = e1, pt.e[2] = e2, pt.e[3] = e3, pt.e[4] = e4;
+    pt.hot = hot;
+    pt.window_bits = c;
+    pt.n_windows = K;
+    pt.rounds = rounds_run;
+    pt.n_adds = n_adds;
   }
+  if (tm) RET_IF(resolve_timing(ctx, tm));
   return 0;
 }
 

@@ -56,10 +56,13 @@ class ShardedMsm:
     def msm(self, scalars, n_local: int, layout: int = 1, on_device: bool = False, window_bits: int = 0):
         """Returns the full MsmResult on rank 0, None elsewhere."""
         with torch.cuda.stream(self.stream):
+            # MSM, collective and combine are ordered on this stream: no host synchronisation in between
             self.engine.run_partial(scalars, n_local, self.partial.data_ptr(), layout=layout,
-                                    window_bits=window_bits, on_device=on_device)
+                                    window_bits=window_bits, on_device=on_device, timing=False)
             if self.world == 1:
                 return self.engine.combine(self.partial.data_ptr(), 1)
             allp = gather_partials(self.partial, self.group)
+            if self.rank == 0:
+                return self.engine.combine(allp.data_ptr(), self.world)
             self.stream.synchronize()
-            return self.engine.combine(allp.data_ptr(), self.world) if self.rank == 0 else None
+            return None

@@ -135,7 +135,10 @@ class MsmEngine:
         return self._result(pt, tm)
 
     def run_partial(self, scalars, n: int, partial_dev_ptr: int, layout: int = L.LAYOUT_LE_BYTES,
-                    form: Optional[int] = None, window_bits: int = 0, on_device: bool = False) -> dict:
+                    form: Optional[int] = None, window_bits: int = 0, on_device: bool = False,
+                    timing: bool = True) -> Optional[dict]:
+        """timing=False: returns without synchronising (the partial is ready in stream order on the engine's
+        stream); fetch the phase timings later with last_timing()."""
         tm = L.Timing()
         if on_device:
             ptr, keep = C.c_void_p(int(scalars)), None
@@ -143,7 +146,13 @@ class MsmEngine:
             ptr, keep = _as_buffer(scalars)
         form = self.default_form if form is None else form
         L.check(self._lib.msm_b200_run_partial(self._ctx, ptr, n, layout, int(on_device), form, window_bits,
-                                               C.c_void_p(partial_dev_ptr), C.byref(tm)), self._ctx)
+                                               C.c_void_p(partial_dev_ptr), C.byref(tm) if timing else None),
+                self._ctx)
+        return tm.as_dict() if timing else None
+
+    def last_timing(self) -> dict:
+        tm = L.Timing()
+        L.check(self._lib.msm_b200_last_timing(self._ctx, C.byref(tm)), self._ctx)
         return tm.as_dict()
 
     def combine(self, partials_dev_ptr: int, count: int) -> MsmResult:

@@ -275,3 +275,33 @@ def test_skewed_scalars_all_equal(mz):
     with mz.MsmEngine("ed-on-bls12-377") as eng:
         r = eng.msm(I.scalars_le([s] * n), I.points_le(pts, 32), n)
         assert (r.x, r.y) == want
+
+
+def test_run_partial_without_sync_and_last_timing(mz):
+    """msm_b200_run_partial(timing = NULL) returns in stream order without a host synchronisation; the combine
+    queued behind it sees the partial, and msm_b200_last_timing() reports the phases of that MSM afterwards.
+    ShardedMsm (world size 1 here) drives exactly that sequence."""
+    from msm_zprize_b200.dist import ShardedMsm
+    params = O.BLS12_377
+    aff = O.WeierstrassAffine(params)
+    n = 300
+    pts = O.random_points_weierstrass(aff, n, seed=77)
+    sc = O.random_scalars(n, params.q, seed=78)
+    want = O.msm(aff, sc, pts)
+    with mz.MsmEngine("bls12-377") as eng:
+        eng.set_bases(I.points_le(pts, 48), n)
+        part = eng.dev_alloc(eng.partial_bytes())
+        assert eng.run_partial(I.scalars_le(sc), n, part, timing=False) is None
+        res = eng.combine(part, 1)
+        assert (res.x, res.y) == want
+        tm = eng.last_timing()
+        assert tm["n_windows"] > 0 and tm["window_bits"] > 0 and tm["kernel_launches"] > 0
+        assert tm["accumulate_ms"] > 0 and tm["reduce_ms"] > 0
+        # with a timing struct the same call synchronises and reports at once
+        tm2 = eng.run_partial(I.scalars_le(sc), n, part)
+        assert tm2["n_windows"] == tm["n_windows"] and tm2["accumulate_ms"] > 0 and tm2["h2d_ms"] >= 0
+    sh = ShardedMsm("bls12-377", device=0)
+    sh.set_bases(I.points_le(pts, 48), n)
+    r = sh.msm(I.scalars_le(sc), n)
+    assert (r.x, r.y) == want
+    sh.engine.close()
