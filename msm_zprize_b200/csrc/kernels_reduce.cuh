@@ -372,11 +372,11 @@ __global__ void k_zero_partial(uint4* __restrict__ partial) {
 // src/curve-projective.ts:335-349, src/field-msm.ts:182-185).
 template <class C>
 __global__ void k_finalize(const uint4* __restrict__ partials, int count, uint32_t* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: every lane quad sums the partials with shared field products (add_quad), lane 0 normalises
   typename C::Acc acc = C::ld(partials);
 #pragma unroll 1
-  for (int i = 1; i < count; i++) acc = C::add(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
-  C::normalise(acc, out);
+  for (int i = 1; i < count; i++) acc = C::add_quad(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
+  if (threadIdx.x == 0 && blockIdx.x == 0) C::normalise(acc, out);
 }
 
 }  // namespace msm
