@@ -296,7 +296,7 @@ def main():
     def step_e2e(s):
         if world == 1:
             return eng.msm(h_sc[s].array, h_pts.array, n, window_bits=args.window)
-        eng.set_bases(h_pts.array, n)
+        eng.set_bases_async(h_pts.array, n)  # overlaps the scalar upload, GLV and sort of the run below
         eng.run_partial(h_sc[s].array, n, partial.data_ptr(), window_bits=args.window, timing=False)
         dist.all_gather_into_tensor(gathered, partial)
         return eng.combine(gathered.data_ptr(), world) if rank == 0 else None

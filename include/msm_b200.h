@@ -110,6 +110,11 @@ const char* msm_b200_global_error(void);
  * and, for LE_BYTES, what Parallel.pointsFromBytes does (src/parallel.ts:97-116,209-232).
  * `points` is host memory unless `on_device` != 0. */
 int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device);
+/* Same for host points, without waiting: the copy and the ingest kernel are queued on the context's copy
+ * stream and the next run / run_partial waits for them only where it first reads a base point, i.e. behind its
+ * own scalar upload, GLV and sort phases (what msm_b200_msm does inside one call).  `points_host` must stay
+ * valid and unchanged until that run has returned; pinned memory makes the copy asynchronous. */
+int msm_b200_set_bases_async(msm_b200_ctx* ctx, const void* points_host, size_t n, int layout);
 
 /* -- the MSM --------------------------------------------------------------------------------
  * replaces Parallel.msm / Parallel.msmUnsafe / Parallel.msmProjective

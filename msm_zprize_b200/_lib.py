@@ -46,7 +46,7 @@ _lib = None
 
 EXPORTS = [
     "msm_b200_create", "msm_b200_destroy", "msm_b200_last_error", "msm_b200_global_error",
-    "msm_b200_set_bases", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial", "msm_b200_last_timing",
+    "msm_b200_set_bases", "msm_b200_set_bases_async", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial", "msm_b200_last_timing",
     "msm_b200_partial_bytes", "msm_b200_combine", "msm_b200_random_points",
     "msm_b200_random_scalars", "msm_b200_point_bytes", "msm_b200_scalar_bytes",
     "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
     L.msm_b200_last_error.restype = C.c_char_p
     L.msm_b200_global_error.restype = C.c_char_p
     L.msm_b200_set_bases.argtypes = [vp, vp, sz, ci, ci]
+    L.msm_b200_set_bases_async.argtypes = [vp, vp, sz, ci]
     L.msm_b200_run.argtypes = [vp, vp, sz, ci, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_msm.argtypes = [vp, vp, ci, vp, ci, sz, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_run_partial.argtypes = [vp, vp, sz, ci, ci, ci, ci, vp, C.POINTER(Timing)]

@@ -212,6 +212,10 @@ int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layo
   return rc;
 }
 
+int msm_b200_set_bases_async(msm_b200_ctx* ctx, const void* points_host, size_t n, int layout) {
+  return set_bases_impl(ctx, points_host, n, layout, 0, /*overlapped=*/true);
+}
+
 int msm_b200_run_partial(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_layout, int on_device, int form,
                          int window_bits, void* partial_dev, msm_b200_timing* timing) {
   if (!partial_dev) return fail(ctx, MSM_E_INVALID, "null partial pointer");

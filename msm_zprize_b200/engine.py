@@ -103,6 +103,13 @@ class MsmEngine:
         ptr, keep = _as_buffer(points)
         L.check(self._lib.msm_b200_set_bases(self._ctx, ptr, n, layout, 0), self._ctx)
 
+    def set_bases_async(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
+        """Queues upload + ingest on the copy stream; the next run()/run_partial() waits for it where it first
+        reads a base point.  `points` must stay alive and unchanged until that run has returned."""
+        ptr, keep = _as_buffer(points)
+        self._pending_points = keep
+        L.check(self._lib.msm_b200_set_bases_async(self._ctx, ptr, n, layout), self._ctx)
+
     def set_bases_device(self, dev_ptr: int, n: int, layout: int = L.LAYOUT_LE_BYTES):
         L.check(self._lib.msm_b200_set_bases(self._ctx, C.c_void_p(dev_ptr), n, layout, 1), self._ctx)
 

@@ -305,3 +305,25 @@ def test_run_partial_without_sync_and_last_timing(mz):
     r = sh.msm(I.scalars_le(sc), n)
     assert (r.x, r.y) == want
     sh.engine.close()
+
+
+def test_set_bases_async_then_run(mz):
+    """msm_b200_set_bases_async: upload + ingest on the copy stream, consumed by the next run (the two-call
+    form of what msm_b200_msm does); a second upload replaces the first."""
+    params = O.PALLAS
+    aff = O.WeierstrassAffine(params)
+    n = 200
+    pts = O.random_points_weierstrass(aff, n, seed=91)
+    pts2 = O.random_points_weierstrass(aff, n, seed=92)
+    sc = O.random_scalars(n, params.q, seed=93)
+    with mz.MsmEngine("pallas") as eng:
+        buf = I.points_le(pts, 32)
+        eng.set_bases_async(buf, n)
+        r = eng.run(I.scalars_le(sc), n)
+        assert (r.x, r.y) == O.msm(aff, sc, pts)
+        buf2 = I.points_le(pts2, 32)
+        eng.set_bases_async(buf2, n)
+        eng.set_bases_async(buf, n)  # never consumed upload is superseded cleanly
+        eng.set_bases_async(buf2, n)
+        r = eng.run(I.scalars_le(sc), n)
+        assert (r.x, r.y) == O.msm(aff, sc, pts2)
