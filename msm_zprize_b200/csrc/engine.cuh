@@ -588,7 +588,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     // pairs per thread: small rounds run as ONE full wave of resident blocks (no tail, few thread
     // totals for the product tree); large rounds as ~ACC_WAVES waves so that dynamic block
     // scheduling evens out the SMs
-    size_t per_wave = (size_t)ACC_RESIDENT * ctx->sm_count * ACC_THREADS;
+    size_t per_wave = (size_t)acc_resident<F>() * ctx->sm_count * ACC_THREADS;
     int B0;
     if (P <= (size_t)ACC_SINGLE_WAVE_MAX) {
       B0 = (int)cdiv(P, per_wave);

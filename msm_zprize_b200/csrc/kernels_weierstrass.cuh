@@ -21,7 +21,15 @@ constexpr int ACC_MIN_PAIRS = 2;  // pairs per thread are chosen per round (Roun
 constexpr int ACC_MAX_PAIRS = 32; //   bounds so that the grid is about ACC_WAVES full waves of blocks
 constexpr int ACC_WAVES = 8;      //   (dynamic block scheduling balances the SMs; few waves leave a tail)
 constexpr int ACC_SINGLE_WAVE_MAX = 4 << 20;  // rounds with at most this many pairs run as one wave
-constexpr int ACC_RESIDENT = 2;   // resident blocks per SM of k_bwd (126 registers x 256 threads)
+constexpr int ACC_RESIDENT = 2;   // resident blocks per SM of k_bwd (126 registers x 256 threads), 12-limb fields
+#ifndef MSM_ACC_RESIDENT_SMALL
+#define MSM_ACC_RESIDENT_SMALL 3
+#endif
+// 8-limb fields: 3 blocks (<= 85 registers); their rounds lean on HBM latency, not only on the IMAD pipe
+template <class F>
+constexpr int acc_resident() {
+  return F::N <= 8 ? MSM_ACC_RESIDENT_SMALL : ACC_RESIDENT;
+}
 constexpr int UP_THREADS = 64;    // block size of the serial product-tree levels
 constexpr int UP_B1 = 8;          // elements per thread, serial levels
 constexpr int TREE_CTA = 256;     // elements per block of the scan-based tree levels (one block per SM:
@@ -500,7 +508,7 @@ __device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i,
 // BLK (small rounds): the block multiplies its thread totals on the spot (block_products), so the
 // product tree starts from one element per block and two kernel launches per round disappear.
 template <class F, bool R0, bool BLK>
-__global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
+__global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_fwd(RoundArgs<F> a) {
   __shared__ uint32_t smem[BLK ? 97 * F::N : 1];
   const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
   const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_fwd(RoundArgs<F> a) {
 
 // backward pass: individual inverses from the running inverse, then finish the additions
 template <class F, bool R0, bool BLK>
-__global__ void __launch_bounds__(ACC_THREADS) k_bwd(RoundArgs<F> a) {
+__global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_bwd(RoundArgs<F> a) {
   const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
   const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
   Fe<F> inv = BLK ? fe_mul(ld_soa<F>(a.invtot, gridDim.x, blockIdx.x), ld_soa<F>(a.tot, a.M1, gid))
