@@ -155,6 +155,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   if (const char* e = getenv("MSM_B200_FINISH_ADD")) ctx->finish_add_modmuls = atof(e);
   if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = atof(e);
   if (const char* e = getenv("MSM_B200_FINISH_ELEMS")) ctx->finish_max_elems = atoi(e);
+  if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = atoi(e);
   if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = atoi(e);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = atoi(e);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)atoll(e);

@@ -52,6 +52,7 @@ struct msm_b200_ctx {
   double finish_add_modmuls = 18.0;
   double finish_round_modmuls = 1.0e6;
   int finish_max_elems = FINISH_MAX_ELEMS;
+  int acc_min_pairs = ACC_MIN_PAIRS;  // MSM_B200_ACC_MIN_PAIRS (tuning)
   int reduce_gb0 = 3;          // MSM_B200_REDUCE_GB0 (tuning)
   int reduce_warp_gb = 3;         // MSM_B200_REDUCE_WARP_GB (2^18 buckets: 5 -> 1.29 ms, 4 -> 1.25, 3 -> 1.22, 2 -> 1.24)
   size_t reduce_warp_min = 4096;  // MSM_B200_REDUCE_WARP_MIN: levels with more items use one lane per item
@@ -592,7 +593,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     int B0;
     if (P <= (size_t)ACC_SINGLE_WAVE_MAX) {
       B0 = (int)cdiv(P, per_wave);
-      if (B0 < ACC_MIN_PAIRS) B0 = ACC_MIN_PAIRS;
+      if (B0 < ctx->acc_min_pairs) B0 = ctx->acc_min_pairs;
     } else {
       B0 = (int)cdiv(P, per_wave * ACC_WAVES);
       if (B0 > ACC_MAX_PAIRS) B0 = ACC_MAX_PAIRS;
