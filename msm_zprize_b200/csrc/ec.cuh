@@ -123,14 +123,14 @@ MSM_HD Proj<F> proj_from_aff(const Aff<F>& A) {
 
 template <class F, uint32_t B3>
 MSM_HD Proj<F> proj_add(const Proj<F>& P, const Proj<F>& Q) {
-  Fe<F> t0 = fe_mul(P.X, Q.X);
-  Fe<F> t1 = fe_mul(P.Y, Q.Y);
-  Fe<F> t2 = fe_mul(P.Z, Q.Z);
-  Fe<F> t3 = fe_mul(fe_add(P.X, P.Y), fe_add(Q.X, Q.Y));
+  Fe<F> t0 = fe_mul_call(P.X, Q.X);
+  Fe<F> t1 = fe_mul_call(P.Y, Q.Y);
+  Fe<F> t2 = fe_mul_call(P.Z, Q.Z);
+  Fe<F> t3 = fe_mul_call(fe_add(P.X, P.Y), fe_add(Q.X, Q.Y));
   t3 = fe_sub(t3, fe_add(t0, t1));
-  Fe<F> t4 = fe_mul(fe_add(P.Y, P.Z), fe_add(Q.Y, Q.Z));
+  Fe<F> t4 = fe_mul_call(fe_add(P.Y, P.Z), fe_add(Q.Y, Q.Z));
   t4 = fe_sub(t4, fe_add(t1, t2));
-  Fe<F> y3 = fe_mul(fe_add(P.X, P.Z), fe_add(Q.X, Q.Z));
+  Fe<F> y3 = fe_mul_call(fe_add(P.X, P.Z), fe_add(Q.X, Q.Z));
   y3 = fe_sub(y3, fe_add(t0, t2));
   t0 = fe_add(fe_dbl(t0), t0);
   t2 = fe_mul_small(t2, B3);
@@ -138,9 +138,9 @@ MSM_HD Proj<F> proj_add(const Proj<F>& P, const Proj<F>& Q) {
   t1 = fe_sub(t1, t2);
   y3 = fe_mul_small(y3, B3);
   Proj<F> R;
-  R.X = fe_sub(fe_mul(t3, t1), fe_mul(t4, y3));
-  R.Y = fe_add(fe_mul(t1, z3), fe_mul(y3, t0));
-  R.Z = fe_add(fe_mul(z3, t4), fe_mul(t0, t3));
+  R.X = fe_sub(fe_mul_call(t3, t1), fe_mul_call(t4, y3));
+  R.Y = fe_add(fe_mul_call(t1, z3), fe_mul_call(y3, t0));
+  R.Z = fe_add(fe_mul_call(z3, t4), fe_mul_call(t0, t3));
   return R;
 }
 
@@ -167,19 +167,19 @@ MSM_HD Proj<F> proj_add_mixed(const Proj<F>& P, const Aff<F>& Q) {
 
 template <class F, uint32_t B3>
 MSM_HD Proj<F> proj_dbl(const Proj<F>& P) {
-  Fe<F> t0 = fe_sqr(P.Y);
+  Fe<F> t0 = fe_sqr_call(P.Y);
   Fe<F> z3 = fe_dbl(fe_dbl(fe_dbl(t0)));  // 8 Y^2
-  Fe<F> t1 = fe_mul(P.Y, P.Z);
-  Fe<F> t2 = fe_mul_small(fe_sqr(P.Z), B3);
-  Fe<F> x3 = fe_mul(t2, z3);
+  Fe<F> t1 = fe_mul_call(P.Y, P.Z);
+  Fe<F> t2 = fe_mul_small(fe_sqr_call(P.Z), B3);
+  Fe<F> x3 = fe_mul_call(t2, z3);
   Fe<F> y3 = fe_add(t0, t2);
-  z3 = fe_mul(t1, z3);
+  z3 = fe_mul_call(t1, z3);
   t2 = fe_add(fe_dbl(t2), t2);
   t0 = fe_sub(t0, t2);
-  y3 = fe_add(x3, fe_mul(t0, y3));
-  t1 = fe_mul(P.X, P.Y);
+  y3 = fe_add(x3, fe_mul_call(t0, y3));
+  t1 = fe_mul_call(P.X, P.Y);
   Proj<F> R;
-  R.X = fe_dbl(fe_mul(t0, t1));
+  R.X = fe_dbl(fe_mul_call(t0, t1));
   R.Y = y3;
   R.Z = z3;
   return R;
@@ -240,16 +240,16 @@ MSM_HD Niels<F> niels_from_xy(const Fe<F>& x, const Fe<F>& y) {
 // P + Q (full, 9M):  src/curve-twisted-edwards.ts:84-165 with mixed = false
 template <class F>
 MSM_HD Ext<F> ext_add(const Ext<F>& P, const Ext<F>& Q) {
-  Fe<F> A = fe_mul(fe_sub(P.Y, P.X), fe_sub(Q.Y, Q.X));
-  Fe<F> B = fe_mul(fe_add(P.Y, P.X), fe_add(Q.Y, Q.X));
-  Fe<F> C = fe_mul(fe_mul(P.T, Q.T), fe_k2d<F>());
-  Fe<F> D = fe_dbl(fe_mul(P.Z, Q.Z));
+  Fe<F> A = fe_mul_call(fe_sub(P.Y, P.X), fe_sub(Q.Y, Q.X));
+  Fe<F> B = fe_mul_call(fe_add(P.Y, P.X), fe_add(Q.Y, Q.X));
+  Fe<F> C = fe_mul_call(fe_mul_call(P.T, Q.T), fe_k2d<F>());
+  Fe<F> D = fe_dbl(fe_mul_call(P.Z, Q.Z));
   Fe<F> E = fe_sub(B, A), Fv = fe_sub(D, C), G = fe_add(D, C), H = fe_add(B, A);
   Ext<F> R;
-  R.X = fe_mul(E, Fv);
-  R.Y = fe_mul(G, H);
-  R.T = fe_mul(E, H);
-  R.Z = fe_mul(Fv, G);
+  R.X = fe_mul_call(E, Fv);
+  R.Y = fe_mul_call(G, H);
+  R.T = fe_mul_call(E, H);
+  R.Z = fe_mul_call(Fv, G);
   return R;
 }
 

@@ -466,6 +466,18 @@ MSM_HD Fe<F> fe_sqr(const Fe<F>& a) {
   return r;
 }
 
+#ifdef __CUDACC__
+template <class F>
+__device__ __noinline__ Fe<F> fe_sqr_call(Fe<F> a) {
+  return fe_sqr(a);
+}
+#else
+template <class F>
+inline Fe<F> fe_sqr_call(const Fe<F>& a) {
+  return fe_sqr(a);
+}
+#endif
+
 // a * (small unsigned constant), by double-and-add on the constant's bits (c >= 1)
 template <class F>
 MSM_HD Fe<F> fe_mul_small(const Fe<F>& a, uint32_t c) {
