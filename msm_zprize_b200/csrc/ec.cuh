@@ -147,21 +147,21 @@ MSM_HD Proj<F> proj_add(const Proj<F>& P, const Proj<F>& Q) {
 // P + Q with Q affine and NOT infinity (callers check the flag)
 template <class F, uint32_t B3>
 MSM_HD Proj<F> proj_add_mixed(const Proj<F>& P, const Aff<F>& Q) {
-  Fe<F> t0 = fe_mul(P.X, Q.x);
-  Fe<F> t1 = fe_mul(P.Y, Q.y);
-  Fe<F> t3 = fe_mul(fe_add(Q.x, Q.y), fe_add(P.X, P.Y));
+  Fe<F> t0 = fe_mul_call(P.X, Q.x);
+  Fe<F> t1 = fe_mul_call(P.Y, Q.y);
+  Fe<F> t3 = fe_mul_call(fe_add(Q.x, Q.y), fe_add(P.X, P.Y));
   t3 = fe_sub(t3, fe_add(t0, t1));
-  Fe<F> t4 = fe_add(fe_mul(Q.y, P.Z), P.Y);
-  Fe<F> y3 = fe_add(fe_mul(Q.x, P.Z), P.X);
+  Fe<F> t4 = fe_add(fe_mul_call(Q.y, P.Z), P.Y);
+  Fe<F> y3 = fe_add(fe_mul_call(Q.x, P.Z), P.X);
   t0 = fe_add(fe_dbl(t0), t0);
   Fe<F> t2 = fe_mul_small(P.Z, B3);
   Fe<F> z3 = fe_add(t1, t2);
   t1 = fe_sub(t1, t2);
   y3 = fe_mul_small(y3, B3);
   Proj<F> R;
-  R.X = fe_sub(fe_mul(t3, t1), fe_mul(t4, y3));
-  R.Y = fe_add(fe_mul(t1, z3), fe_mul(y3, t0));
-  R.Z = fe_add(fe_mul(z3, t4), fe_mul(t0, t3));
+  R.X = fe_sub(fe_mul_call(t3, t1), fe_mul_call(t4, y3));
+  R.Y = fe_add(fe_mul_call(t1, z3), fe_mul_call(y3, t0));
+  R.Z = fe_add(fe_mul_call(z3, t4), fe_mul_call(t0, t3));
   return R;
 }
 
