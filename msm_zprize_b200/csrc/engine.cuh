@@ -344,6 +344,9 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   const uint32_t L = 1u << (c - 1);
   const size_t NB = (size_t)K * L;
   if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
+  // sorted-entry slots are addressed with 32 bits (2 * pair offset + position)
+  if ((unsigned long long)n * K >= (1ull << 31))
+    return fail(ctx, MSM_E_INVALID, "too many digit entries for one context (n * windows >= 2^31): shard the points");
   int e0 = T.mark();
   RET_IF(ensure(ctx, ctx->hs, n * 32));
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
@@ -471,6 +474,9 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   const size_t NB = (size_t)K * L;
   const size_t S = 2 * n;
   if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
+  // sorted-entry slots are addressed with 32 bits (2 * pair offset + position)
+  if ((unsigned long long)S * K >= (1ull << 31))
+    return fail(ctx, MSM_E_INVALID, "too many digit entries for one context (2n * windows >= 2^31): shard the points");
 
   int e0 = T.mark();
   // --- GLV + digits + histogram

@@ -327,3 +327,19 @@ def test_set_bases_async_then_run(mz):
         eng.set_bases_async(buf2, n)
         r = eng.run(I.scalars_le(sc), n)
         assert (r.x, r.y) == O.msm(aff, sc, pts2)
+
+
+def test_entry_count_limit_is_an_error_not_an_overflow(mz):
+    """Sorted entries are addressed with 32 bits: a call whose digit count reaches 2^31 must fail loudly."""
+    n = (1 << 23) + (1 << 17)  # 2n * 127 one-bit windows = 2.16e9 >= 2^31
+    with mz.MsmEngine("bls12-377") as eng:
+        d_pts = eng.dev_alloc(n * 96)
+        d_sc = eng.dev_alloc(n * 32)
+        eng.random_points_device(d_pts, 1 << 10, 1)   # contents do not matter: the check precedes any work
+        eng.random_scalars_device(d_sc, 1 << 10, 2)
+        eng.set_bases_device(d_pts, n)
+        with pytest.raises(mz.MsmError) as e:
+            eng.run(d_sc, n, on_device=True, window_bits=1)
+        assert e.value.code == -1  # MSM_E_INVALID
+        r = eng.run(d_sc, 1 << 10, on_device=True)             # the context stays usable
+        assert not r.is_zero
