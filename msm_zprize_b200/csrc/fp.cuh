@@ -478,6 +478,45 @@ inline Fe<F> fe_sqr_call(const Fe<F>& a) {
 }
 #endif
 
+// ------------------------------------------------------------------------------------------
+// Unreduced ("lazy") helpers for fields with F::LAZY (floor(2^(32N) / p) >= 64, i.e. BLS12-377 Fq with its 7
+// spare bits).  Values are bounded multiples of p that still fit the limbs; no conditional subtraction, and
+// the shifts have no carry chain at all.  fe_mul / fe_sqr accept such operands as long as
+// (a/p) * (b/p) < floor(2^(32N) / p) and return a canonical value.  Used by the one-warp tail only
+// (kernels_reduce.cuh), where every dependent instruction costs ~4.5 cycles.
+// ------------------------------------------------------------------------------------------
+template <class F>
+MSM_HD Fe<F> fe_add_nr(const Fe<F>& a, const Fe<F>& b) {  // a + b, caller guarantees a + b < 2^(32N)
+  Fe<F> r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < F::N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  r.v[F::N - 1] = addc(a.v[F::N - 1], b.v[F::N - 1]);
+  return r;
+}
+
+template <class F, int S>
+MSM_HD Fe<F> fe_shl_nr(const Fe<F>& a) {  // a * 2^S, S in 1..3, no overflow by the caller's bound
+  Fe<F> r;
+#pragma unroll
+  for (int i = F::N - 1; i >= 1; i--) r.v[i] = (a.v[i] << S) | (a.v[i - 1] >> (32 - S));
+  r.v[0] = a.v[0] << S;
+  return r;
+}
+
+// a - b + K p for K in {1, 2, 3, 9}: positive whenever b < K p
+template <class F, int K>
+MSM_HD Fe<F> fe_sub_nr(const Fe<F>& a, const Fe<F>& b) {
+  Fe<F> t;
+  t.v[0] = sub_cc(K == 1 ? F::P(0) : (K == 2 ? F::P2(0) : (K == 3 ? F::P3(0) : F::P9(0))), b.v[0]);
+#pragma unroll
+  for (int i = 1; i < F::N - 1; i++)
+    t.v[i] = subc_cc(K == 1 ? F::P(i) : (K == 2 ? F::P2(i) : (K == 3 ? F::P3(i) : F::P9(i))), b.v[i]);
+  t.v[F::N - 1] = subc(K == 1 ? F::P(F::N - 1) : (K == 2 ? F::P2(F::N - 1) : (K == 3 ? F::P3(F::N - 1) : F::P9(F::N - 1))),
+                       b.v[F::N - 1]);
+  return fe_add_nr(a, t);
+}
+
 // a * (small unsigned constant), by double-and-add on the constant's bits (c >= 1)
 template <class F>
 MSM_HD Fe<F> fe_mul_small(const Fe<F>& a, uint32_t c) {

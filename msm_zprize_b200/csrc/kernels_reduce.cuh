@@ -85,6 +85,60 @@ struct WeierCurve {
     return proj_add_mixed<F, B3_>(a, Q);
   }
   // quad-cooperative doubling / addition (same formulas as proj_dbl / proj_add, RCB16 alg. 9 / 7)
+  // Unreduced variants for F::LAZY fields with b3 = 3 (BLS12-377): coordinates are kept < 2p between
+  // operations and every product below multiplies operands of at most 10p x 4p, 9p x 3p (< 152 p^2 / p).
+  __device__ static Acc dbl_quad_lazy(const Acc& P) {
+    Fe<F> t0, t1, t2, xy;
+    quad_mul4<F>(P.Y, P.Y, P.Y, P.Z, P.Z, P.Z, P.X, P.Y, t0, t1, t2, xy);  // inputs < 2p, outputs < p
+    Fe<F> z3 = fe_shl_nr<F, 3>(t0);                      // 8 t0          < 8p
+    Fe<F> t2b = fe_add_nr(fe_shl_nr<F, 1>(t2), t2);      // b3 t2 = 3 t2  < 3p
+    Fe<F> y3 = fe_add_nr(t0, t2b);                       //               < 4p
+    Fe<F> t23 = fe_add_nr(fe_shl_nr<F, 1>(t2b), t2b);    // 3 * (3 t2)    < 9p
+    Fe<F> t0b = fe_sub_nr<F, 9>(t0, t23);                // t0 - t23 + 9p < 10p
+    Fe<F> x3, zz, yy, xx;
+    quad_mul4<F>(z3, t2b, z3, t1, t0b, y3, t0b, xy, x3, zz, yy, xx);
+    Acc R;
+    R.X = fe_shl_nr<F, 1>(xx);   // < 2p
+    R.Y = fe_add_nr(x3, yy);     // < 2p
+    R.Z = zz;                    // < p
+    return R;
+  }
+  __device__ static Acc add_quad_lazy(const Acc& P, const Acc& Q) {
+    Fe<F> t0, t1, t2, t3, t4, y3, d0, d1;
+    quad_mul4<F>(P.X, Q.X, P.Y, Q.Y, P.Z, Q.Z, fe_add_nr(P.X, P.Y), fe_add_nr(Q.X, Q.Y), t0, t1, t2, t3);  // 4p x 4p
+    quad_mul4<F>(fe_add_nr(P.Y, P.Z), fe_add_nr(Q.Y, Q.Z), fe_add_nr(P.X, P.Z), fe_add_nr(Q.X, Q.Z), P.X, P.X, P.X,
+                 P.X, t4, y3, d0, d1);
+    t3 = fe_sub_nr<F, 2>(t3, fe_add_nr(t0, t1));          // < 3p
+    t4 = fe_sub_nr<F, 2>(t4, fe_add_nr(t1, t2));          // < 3p
+    y3 = fe_sub_nr<F, 2>(y3, fe_add_nr(t0, t2));          // < 3p
+    t0 = fe_add_nr(fe_shl_nr<F, 1>(t0), t0);              // 3 t0 < 3p
+    t2 = fe_add_nr(fe_shl_nr<F, 1>(t2), t2);              // b3 t2 < 3p
+    Fe<F> z3 = fe_add_nr(t1, t2);                         // < 4p
+    t1 = fe_sub_nr<F, 3>(t1, t2);                         // < 4p
+    y3 = fe_add_nr(fe_shl_nr<F, 1>(y3), y3);              // b3 y3 < 9p
+    Fe<F> a, b, c, d, e, f;
+    quad_mul4<F>(t1, t3, y3, t4, t1, z3, y3, t0, a, b, c, d);   // 4x3, 9x3, 4x4, 9x3
+    quad_mul4<F>(z3, t4, t0, t3, t0, t0, t0, t0, e, f, d0, d1);
+    Acc R;
+    R.X = fe_sub_nr<F, 1>(a, b);  // < 2p
+    R.Y = fe_add_nr(c, d);        // < 2p
+    R.Z = fe_add_nr(e, f);        // < 2p
+    return R;
+  }
+  // canonical representative of a point whose coordinates are < 2p (before it is stored or compared)
+  __device__ static Acc canon(const Acc& P) {
+    Acc R = P;
+    if (QUAD_LAZY) {
+      fe_reduce_once(R.X);
+      fe_reduce_once(R.Y);
+      fe_reduce_once(R.Z);
+    }
+    return R;
+  }
+  static constexpr bool QUAD_LAZY = F::LAZY && B3_ == 3;
+  // quad ops on values < 2p with results < 2p when QUAD_LAZY (canon() before storing), canonical otherwise
+  __device__ static Acc dblq(const Acc& P) { return QUAD_LAZY ? dbl_quad_lazy(P) : dbl_quad(P); }
+  __device__ static Acc addq(const Acc& P, const Acc& Q) { return QUAD_LAZY ? add_quad_lazy(P, Q) : add_quad(P, Q); }
   __device__ static Acc dbl_quad(const Acc& P) {
     Fe<F> t0, t1, t2, xy;
     quad_mul4<F>(P.Y, P.Y, P.Y, P.Z, P.Z, P.Z, P.X, P.Y, t0, t1, t2, xy);
@@ -182,6 +236,9 @@ struct TeCurve {
   }
   // quad-cooperative doubling (dedicated a = -1 formula dbl-2008-hwcd: 4M + 4S in 2 layers; the
   // reference doubles with the unified addition, src/curve-twisted-edwards.ts:215-227 -- same point)
+  __device__ static Acc dblq(const Acc& P) { return dbl_quad(P); }
+  __device__ static Acc addq(const Acc& P, const Acc& Q) { return add_quad(P, Q); }
+  __device__ static Acc canon(const Acc& P) { return P; }
   __device__ static Acc dbl_quad(const Acc& P) {
     Fe<F> A, B, ZZ, S;
     quad_mul4<F>(P.X, P.X, P.Y, P.Y, P.Z, P.Z, fe_add(P.X, P.Y), fe_add(P.X, P.Y), A, B, ZZ, S);
@@ -329,24 +386,24 @@ __global__ void __launch_bounds__(64) k_reduce_quad(const uint4* __restrict__ in
   Acc Y = live ? C::ld(p + item_u4<C>() / 2) : C::zero();
 #pragma unroll 1
   for (int d = 1; d < g; d <<= 1) {
-    Acc n = C::add_quad(S, C::shfl_down(S, 4 * d));
+    Acc n = C::addq(S, C::shfl_down(S, 4 * d));
     if (j + d < g) S = n;
   }
   {
-    Acc n = C::add_quad(Y, S);
+    Acc n = C::addq(Y, S);
     if (j >= 1) Y = n;
   }
 #pragma unroll 1
   for (int d = g >> 1; d >= 1; d >>= 1) {
-    Acc n = C::add_quad(Y, C::shfl_down(Y, 4 * d));
+    Acc n = C::addq(Y, C::shfl_down(Y, 4 * d));
     if (j < d) Y = n;
   }
 #pragma unroll 1
-  for (int d = 0; d < gb; d++) S = C::dbl_quad(S);
+  for (int d = 0; d < gb; d++) S = C::dblq(S);
   if (live && j == 0 && (t & 3) == 0) {
     uint4* o = out + (size_t)(i >> gb) * item_u4<C>();
-    C::st(o, S);
-    C::st(o + item_u4<C>() / 2, Y);
+    C::st(o, C::canon(S));
+    C::st(o + item_u4<C>() / 2, C::canon(Y));
   }
 }
 
@@ -357,10 +414,10 @@ __global__ void __launch_bounds__(32) k_horner(const uint4* __restrict__ items, 
 #pragma unroll 1
   for (int k = K - 2; k >= 0; k--) {
 #pragma unroll 1
-    for (int d = 0; d < c; d++) acc = C::dbl_quad(acc);
-    acc = C::add_quad(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
+    for (int d = 0; d < c; d++) acc = C::dblq(acc);
+    acc = C::addq(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
   }
-  if (threadIdx.x == 0) C::st(partial, acc);
+  if (threadIdx.x == 0) C::st(partial, C::canon(acc));
 }
 
 template <class C>
@@ -375,8 +432,8 @@ __global__ void k_finalize(const uint4* __restrict__ partials, int count, uint32
   // one warp: every lane quad sums the partials with shared field products (add_quad), lane 0 normalises
   typename C::Acc acc = C::ld(partials);
 #pragma unroll 1
-  for (int i = 1; i < count; i++) acc = C::add_quad(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
-  if (threadIdx.x == 0 && blockIdx.x == 0) C::normalise(acc, out);
+  for (int i = 1; i < count; i++) acc = C::addq(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
+  if (threadIdx.x == 0 && blockIdx.x == 0) C::normalise(C::canon(acc), out);
 }
 
 }  // namespace msm

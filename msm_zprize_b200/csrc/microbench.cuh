@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) k_mb_dbl_chain(uint32_t* out, int iters, u
   acc.Y.v[1] = 5u;
   acc.Z.v[0] = 1u;
 #pragma unroll 1
-  for (int it = 0; it < iters; it++) acc = QUAD ? C::dbl_quad(acc) : C::dbl(acc);
+  for (int it = 0; it < iters; it++) acc = QUAD ? C::dblq(acc) : C::dbl(acc);
   uint32_t x = 0;
 #pragma unroll
   for (int j = 0; j < C::F::N; j++) x ^= acc.X.v[j] ^ acc.Y.v[j] ^ acc.Z.v[j];

@@ -77,6 +77,12 @@ def field_struct(name, p, n32, extra=None, w29_extra_bits=2):
     s += arr("R2", limbs(R * R % p, n32))
     s += arr("R3", limbs(R * R * R % p, n32))
     s += arr("PM2", limbs(p - 2, n32))
+    # Unreduced ("lazy") arithmetic in the one-warp tail: with SPARE = floor(2^(32 n) / p) >= 64 sums of a few
+    # dozen p still fit the limbs and fe_mul reduces any a * b with (a/p)(b/p) < SPARE.  k*p for a - b + k*p.
+    spare = R // p
+    s += "  static constexpr bool LAZY = %s;  // floor(2^%d / p) = %d\n" % ("true" if spare >= 64 else "false", rbits, spare)
+    for k in (2, 3, 9):
+        s += arr("P%d" % k, limbs(k * p if k * p < R else 0, n32))
     # limb29 Montgomery (R29 = 2^(29 n29)) <-> limb32 Montgomery conversion multipliers
     s += arr("FROM29", limbs(pow(2, 2 * rbits - 29 * n29, p), n32))
     s += arr("TO29", limbs(pow(2, 29 * n29, p), n32))
