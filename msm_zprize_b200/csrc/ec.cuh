@@ -186,6 +186,88 @@ MSM_HD Proj<F> proj_dbl(const Proj<F>& P) {
 }
 
 // (X/Z, Y/Z), infinity if Z == 0   (src/curve-projective.ts:335-349)
+// ------------------------------------------------------------------------------------------
+// The same three formulas with unreduced field additions, for F::LAZY fields with b3 = 3 (BLS12-377 Fq:
+// floor(2^384 / p) = 152).  Contract: coordinates in AND out are < 2p (affine operands canonical); every
+// product multiplies operands a < 10p (the full-width one) and b with (a/p)(b/p) <= 70 < 152, so fe_mul returns
+// canonical values; differences add the multiple of p noted beside them.  Callers canonicalise (proj_canon)
+// before a value is stored, compared or inverted.
+// ------------------------------------------------------------------------------------------
+template <class F>
+MSM_HD Fe<F> fe_x3_nr(const Fe<F>& a) {  // 3a
+  return fe_add_nr(fe_shl_nr<F, 1>(a), a);
+}
+
+template <class F>
+MSM_HD Proj<F> proj_add_nr(const Proj<F>& P, const Proj<F>& Q) {
+  Fe<F> t0 = fe_mul_call(P.X, Q.X);
+  Fe<F> t1 = fe_mul_call(P.Y, Q.Y);
+  Fe<F> t2 = fe_mul_call(P.Z, Q.Z);
+  Fe<F> t3 = fe_mul_call(fe_add_nr(P.X, P.Y), fe_add_nr(Q.X, Q.Y));  // 4p x 4p
+  t3 = fe_sub_nr<F, 2>(t3, fe_add_nr(t0, t1));                        // < 3p
+  Fe<F> t4 = fe_mul_call(fe_add_nr(P.Y, P.Z), fe_add_nr(Q.Y, Q.Z));
+  t4 = fe_sub_nr<F, 2>(t4, fe_add_nr(t1, t2));                        // < 3p
+  Fe<F> y3 = fe_mul_call(fe_add_nr(P.X, P.Z), fe_add_nr(Q.X, Q.Z));
+  y3 = fe_sub_nr<F, 2>(y3, fe_add_nr(t0, t2));                        // < 3p
+  t0 = fe_x3_nr(t0);                                                  // < 3p
+  t2 = fe_x3_nr(t2);                                                  // b3 t2 < 3p
+  Fe<F> z3 = fe_add_nr(t1, t2);                                       // < 4p
+  t1 = fe_sub_nr<F, 3>(t1, t2);                                       // < 4p
+  y3 = fe_x3_nr(y3);                                                  // b3 y3 < 9p
+  Proj<F> R;
+  R.X = fe_sub_nr<F, 1>(fe_mul_call(t1, t3), fe_mul_call(y3, t4));    // 4x3, 9x3
+  R.Y = fe_add_nr(fe_mul_call(t1, z3), fe_mul_call(y3, t0));          // 4x4, 9x3
+  R.Z = fe_add_nr(fe_mul_call(z3, t4), fe_mul_call(t0, t3));          // 4x3, 3x3
+  return R;
+}
+
+// Q affine, canonical, not infinity
+template <class F>
+MSM_HD Proj<F> proj_add_mixed_nr(const Proj<F>& P, const Aff<F>& Q) {
+  Fe<F> t0 = fe_mul_call(P.X, Q.x);
+  Fe<F> t1 = fe_mul_call(P.Y, Q.y);
+  Fe<F> t3 = fe_mul_call(fe_add_nr(P.X, P.Y), fe_add_nr(Q.x, Q.y));   // 4p x 2p
+  t3 = fe_sub_nr<F, 2>(t3, fe_add_nr(t0, t1));                         // < 3p
+  Fe<F> t4 = fe_add_nr(fe_mul_call(P.Z, Q.y), P.Y);                    // < 3p
+  Fe<F> y3 = fe_add_nr(fe_mul_call(P.Z, Q.x), P.X);                    // < 3p
+  t0 = fe_x3_nr(t0);                                                   // < 3p
+  Fe<F> t2 = fe_x3_nr(P.Z);                                            // b3 Z < 6p
+  Fe<F> z3 = fe_add_nr(t1, t2);                                        // < 7p
+  t1 = fe_sub_nr<F, 9>(t1, t2);                                        // < 10p
+  y3 = fe_x3_nr(y3);                                                   // < 9p
+  Proj<F> R;
+  R.X = fe_sub_nr<F, 1>(fe_mul_call(t1, t3), fe_mul_call(y3, t4));     // 10x3, 9x3
+  R.Y = fe_add_nr(fe_mul_call(t1, z3), fe_mul_call(y3, t0));           // 10x7, 9x3
+  R.Z = fe_add_nr(fe_mul_call(z3, t4), fe_mul_call(t0, t3));           // 7x3, 3x3
+  return R;
+}
+
+template <class F>
+MSM_HD Proj<F> proj_dbl_nr(const Proj<F>& P) {
+  Fe<F> t0 = fe_sqr_call(P.Y);
+  Fe<F> z3 = fe_shl_nr<F, 3>(t0);                      // 8 t0 < 8p
+  Fe<F> t1 = fe_mul_call(P.Y, P.Z);
+  Fe<F> t2 = fe_x3_nr(fe_sqr_call(P.Z));               // b3 Z^2 < 3p
+  Fe<F> x3 = fe_mul_call(z3, t2);                      // 8x3
+  Fe<F> y3 = fe_add_nr(t0, t2);                        // < 4p
+  Fe<F> zz = fe_mul_call(z3, t1);                      // 8x1
+  Fe<F> t0b = fe_sub_nr<F, 9>(t0, fe_x3_nr(t2));       // t0 - 3 t2 + 9p < 10p
+  Proj<F> R;
+  R.Y = fe_add_nr(x3, fe_mul_call(t0b, y3));           // 10x4
+  R.X = fe_shl_nr<F, 1>(fe_mul_call(t0b, fe_mul_call(P.X, P.Y)));
+  R.Z = zz;
+  return R;
+}
+
+template <class F>
+MSM_HD Proj<F> proj_canon(const Proj<F>& P) {  // coordinates < 2p -> [0, p)
+  Proj<F> R = P;
+  fe_reduce_once(R.X);
+  fe_reduce_once(R.Y);
+  fe_reduce_once(R.Z);
+  return R;
+}
+
 template <class F>
 MSM_HD Aff<F> proj_to_aff(const Proj<F>& P) {
   if (fe_is_zero(P.Z)) return aff_inf<F>();

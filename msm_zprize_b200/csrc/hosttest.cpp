@@ -38,7 +38,7 @@ static int fe_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   return 0;
 }
 
-// op 0: complete add, 1: mixed add (Q affine = (X,Y) of q), 2: double
+// op 0: complete add, 1: mixed add (Q affine = (X,Y) of q), 2: double, 3: to affine, 4-6: unreduced add / mixed / double
 template <class F, uint32_t B3>
 static int proj_op(int op, const uint32_t* p, const uint32_t* q, uint32_t* out) {
   constexpr int N = F::N;
@@ -48,6 +48,17 @@ static int proj_op(int op, const uint32_t* p, const uint32_t* q, uint32_t* out) 
   if (op == 0) R = proj_add<F, B3>(P, Q);
   else if (op == 1) R = proj_add_mixed<F, B3>(P, Aff<F>{Q.X, Q.Y});
   else if (op == 2) R = proj_dbl<F, B3>(P);
+  else if (op >= 4 && op <= 6) {  // unreduced variants (F::LAZY, b3 = 3); op 7: the same after proj_canon
+    if constexpr (F::LAZY && B3 == 3) {
+      if (op == 4) R = proj_add_nr<F>(P, Q);
+      else if (op == 5) R = proj_add_mixed_nr<F>(P, Aff<F>{Q.X, Q.Y});
+      else R = proj_dbl_nr<F>(P);
+      // contract: coordinates < 2p; report a violation instead of a value
+      Proj<F> C = proj_canon(R);
+      Proj<F> C2 = proj_canon(C);
+      if (!fe_eq(C.X, C2.X) || !fe_eq(C.Y, C2.Y) || !fe_eq(C.Z, C2.Z)) return -2;
+    } else return -1;
+  }
   else if (op == 3) {
     Aff<F> A = proj_to_aff(P);
     R.X = A.x; R.Y = A.y; R.Z = fe_zero<F>();

@@ -226,7 +226,7 @@ __global__ void k_rp_tables(uint4* __restrict__ tables, uint64_t seed) {
   bool started = false;
 #pragma unroll 1
   for (int bit = 79; bit >= 0; bit--) {
-    if (started) acc = C::dbl(acc);
+    if (started) acc = C::canon(C::dbl(acc));  // the generator works on canonical values throughout
     if ((sc >> bit) & 1) {
       acc = AddXY<C>::run(acc, gx, gy);
       started = true;

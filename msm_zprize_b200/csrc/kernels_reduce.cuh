@@ -49,10 +49,19 @@ struct WeierCurve {
   static constexpr int ACC_FE = 3;   // field elements per accumulator
   static constexpr int BASE_FE = 2;  // field elements per cached base point (x | y)
   static constexpr int BASE_STRIDE = 2;  // records per input point in ctx->bases (G, endo G)
+  // QUAD_LAZY (BLS12-377): accumulators held in registers have coordinates < 2p and all additions below are
+  // the unreduced variants (ec.cuh proj_*_nr); memory always holds canonical values (st canonicalises).
   __device__ static Acc zero() { return proj_zero<F>(); }
-  __device__ static Acc add(const Acc& a, const Acc& b) { return proj_add<F, B3_>(a, b); }
-  __device__ static Acc dbl(const Acc& a) { return proj_dbl<F, B3_>(a); }
-  __device__ static void st(uint4* p, const Acc& P) {
+  __device__ static Acc add(const Acc& a, const Acc& b) {
+    if constexpr (F::LAZY && B3_ == 3) return proj_add_nr<F>(a, b);
+    else return proj_add<F, B3_>(a, b);
+  }
+  __device__ static Acc dbl(const Acc& a) {
+    if constexpr (F::LAZY && B3_ == 3) return proj_dbl_nr<F>(a);
+    else return proj_dbl<F, B3_>(a);
+  }
+  __device__ static void st(uint4* p, const Acc& P0) {
+    const Acc P = canon(P0);
     st_aos<F>(p, P.X);
     st_aos<F>(p + F::N / 4, P.Y);
     st_aos<F>(p + 2 * F::N / 4, P.Z);
@@ -82,7 +91,8 @@ struct WeierCurve {
     Q.y = ld_aos<F>(p + F::N / 4);
     if (aff_is_inf(Q)) return a;
     if (neg) Q.y = fe_neg(Q.y);
-    return proj_add_mixed<F, B3_>(a, Q);
+    if constexpr (F::LAZY && B3_ == 3) return proj_add_mixed_nr<F>(a, Q);
+    else return proj_add_mixed<F, B3_>(a, Q);
   }
   // quad-cooperative doubling / addition (same formulas as proj_dbl / proj_add, RCB16 alg. 9 / 7)
   // Unreduced variants for F::LAZY fields with b3 = 3 (BLS12-377): coordinates are kept < 2p between
@@ -289,7 +299,9 @@ struct AffineBucketLoader {
     Aff<F> A;
     A.x = ld_soa<F>(fin, cap, b);
     A.y = ld_soa<F>(fin + (size_t)(F::N / 4) * cap, cap, b);
-    if (!aff_is_inf(A)) run = proj_add_mixed<F, B3>(run, A);
+    if (aff_is_inf(A)) return;
+    if constexpr (F::LAZY && B3 == 3) run = proj_add_mixed_nr<F>(run, A);
+    else run = proj_add_mixed<F, B3>(run, A);
   }
 };
 
@@ -402,8 +414,8 @@ __global__ void __launch_bounds__(64) k_reduce_quad(const uint4* __restrict__ in
   for (int d = 0; d < gb; d++) S = C::dblq(S);
   if (live && j == 0 && (t & 3) == 0) {
     uint4* o = out + (size_t)(i >> gb) * item_u4<C>();
-    C::st(o, C::canon(S));
-    C::st(o + item_u4<C>() / 2, C::canon(Y));
+    C::st(o, S);
+    C::st(o + item_u4<C>() / 2, Y);
   }
 }
 
@@ -417,7 +429,7 @@ __global__ void __launch_bounds__(32) k_horner(const uint4* __restrict__ items, 
     for (int d = 0; d < c; d++) acc = C::dblq(acc);
     acc = C::addq(acc, C::ld(items + (size_t)k * item_u4<C>() + item_u4<C>() / 2));
   }
-  if (threadIdx.x == 0) C::st(partial, C::canon(acc));
+  if (threadIdx.x == 0) C::st(partial, acc);
 }
 
 template <class C>

@@ -592,8 +592,11 @@ __global__ void __launch_bounds__(64) k_finish(RoundArgs<F> a, uint32_t NB, uint
 #pragma unroll 1
     for (uint32_t j = 1; j < n; j++) {
       Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
-      if (!aff_is_inf(Q)) acc = proj_add_mixed<F, B3>(acc, Q);
+      if (aff_is_inf(Q)) continue;
+      if constexpr (F::LAZY && B3 == 3) acc = proj_add_mixed_nr<F>(acc, Q);  // coordinates < 2p in registers
+      else acc = proj_add_mixed<F, B3>(acc, Q);
     }
+    if constexpr (F::LAZY && B3 == 3) acc = proj_canon(acc);
   }
   st_aos<F>(o, acc.X);
   st_aos<F>(o + F::N / 4, acc.Y);

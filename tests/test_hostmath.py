@@ -139,6 +139,23 @@ def test_projective_complete_formulas(lib, field, params, b3):
             assert dec(out) == aff.add(P, Q)
         assert lib.ht_proj_op(field, 2, enc(P), enc(P), out) == 0
         assert dec(out) == aff.double(P)
+        if field == 0:
+            # unreduced variants (BLS12-377: 7 spare bits), canonical operands and operands shifted by p (< 2p)
+            def up(buf, mask):
+                vals_ = [val(buf[i * n:(i + 1) * n]) for i in range(3)]
+                vals_ = [v + p if (mask >> i) & 1 else v for i, v in enumerate(vals_)]
+                words = []
+                for v in vals_:
+                    words += [(v >> (32 * k)) & 0xFFFFFFFF for k in range(n)]
+                return (ctypes.c_uint32 * len(words))(*words)
+            for mp, mq in [(0, 0), (7, 7), (5, 2), (2, 5)]:
+                assert lib.ht_proj_op(field, 4, up(enc(P), mp), up(enc(Q), mq), out) == 0
+                assert dec(out) == aff.add(P, Q)
+                if Q is not None:
+                    assert lib.ht_proj_op(field, 5, up(enc(P), mp), enc(Q, 1), out) == 0
+                    assert dec(out) == aff.add(P, Q)
+                assert lib.ht_proj_op(field, 6, up(enc(P), mp), enc(P), out) == 0
+                assert dec(out) == aff.double(P)
         # to_affine (uses fe_inv)
         assert lib.ht_proj_op(field, 3, enc(P), enc(P), out) == 0
         if P is None:
