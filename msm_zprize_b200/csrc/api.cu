@@ -170,7 +170,8 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
     ctx->own_stream = true;
   }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->bases_ready, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->bases_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->totals_ready, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, MSM_E_CUDA, "stream / event creation failed");
   }
@@ -201,6 +202,7 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->bases_ready) cudaEventDestroy(ctx->bases_ready);
+  if (ctx->totals_ready) cudaEventDestroy(ctx->totals_ready);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

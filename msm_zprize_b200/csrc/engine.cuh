@@ -44,6 +44,7 @@ struct msm_b200_ctx {
   // being decomposed and sorted; the first kernel that reads the bases waits for this event
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t bases_ready = nullptr;
+  cudaEvent_t totals_ready = nullptr;  // bucket totals have reached the pinned host buffer
   bool bases_pending = false;
   std::string err;
   int launches = 0;
@@ -387,7 +388,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
     RET_IF(ensure(ctx, ctx->pairkey[0], (V + 1) * 4));
     RET_IF(ensure(ctx, ctx->elem[0], (V + 1) * C::ACC_FE * FE));
     LAUNCH(ctx, k_fill_pairkey, cdiv((NB + 31) / 32 * 32, 256), 256, (const uint32_t*)ctx->po.p + NB, (uint32_t)NB,
-           (uint32_t)V, (uint32_t*)ctx->pairkey[0].p);
+           (const unsigned long long*)ctx->totals.p + 1 /* = V */, (uint32_t*)ctx->pairkey[0].p);
   }
   int h0 = T.mark();
   if (split) {
@@ -502,17 +503,31 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   sa.digits = digits_dump_dev;
   LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
   int e1 = T.mark();
-  // --- offsets for every round, one host sync
+  // --- offsets for every round; the host needs the totals (one sync), the scatter does not: it is queued
+  //     first, sized by the upper bound 2 * P0 <= S * K + NB, so the GPU keeps working while the host wakes up
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
   RET_IF(launch_scan(ctx, NB, MAX_ROUNDS + 1));
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventRecord(ctx->totals_ready, ctx->stream));
+  if (!digits_dump_dev) {
+    const size_t slots_max = S * (size_t)K + NB + 2;
+    RET_IF(ensure(ctx, ctx->ent, slots_max * 4));
+    RET_IF(ensure(ctx, ctx->pairkey[0], (slots_max / 2 + 2) * 4));
+    sa.ent = (uint32_t*)ctx->ent.p;
+    sa.pairkey = (uint32_t*)ctx->pairkey[0].p;
+    CK(cudaMemsetAsync(ctx->ent.p, 0, slots_max * 4, ctx->stream));  // padding slots are read (and discarded)
+    LAUNCH(ctx, k_hist_scatter<true>, cdiv(S, 256), 256, sa);
+    LAUNCH(ctx, k_fill_pairkey, cdiv((NB + 31) / 32 * 32, 256), 256, (const uint32_t*)ctx->po.p, (uint32_t)NB,
+           (const unsigned long long*)ctx->totals.p, (uint32_t*)ctx->pairkey[0].p);
+  }
+  CK(cudaEventSynchronize(ctx->totals_ready));
   const unsigned long long maxcnt = ctx->h_totals[MAX_ROUNDS + 1];
   int R = 1;
   while (((unsigned long long)1 << R) < maxcnt) R++;
   if (R > MAX_ROUNDS - 1) return fail(ctx, MSM_E_INVALID, "bucket too large");
   const size_t P0 = ctx->h_totals[0];
   if (digits_dump_dev) {  // tests only need the digits
+    CK(cudaStreamSynchronize(ctx->stream));
     if (tm) {
       tm->window_bits = c;
       tm->n_windows = K;
@@ -528,16 +543,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     }
     return 0;
   }
-  // --- scatter
-  RET_IF(ensure(ctx, ctx->ent, (2 * P0 + 2) * 4));
-  RET_IF(ensure(ctx, ctx->pairkey[0], (P0 + 1) * 4));
   RET_IF(ensure(ctx, ctx->pairkey[1], (ctx->h_totals[1] + 1) * 4));
-  sa.ent = (uint32_t*)ctx->ent.p;
-  sa.pairkey = (uint32_t*)ctx->pairkey[0].p;
-  CK(cudaMemsetAsync(ctx->ent.p, 0, (2 * P0 + 2) * 4, ctx->stream));  // padding slots are read (and discarded)
-  LAUNCH(ctx, k_hist_scatter<true>, cdiv(S, 256), 256, sa);
-  LAUNCH(ctx, k_fill_pairkey, cdiv((NB + 31) / 32 * 32, 256), 256, (const uint32_t*)ctx->po.p, (uint32_t)NB, (uint32_t)P0,
-         (uint32_t*)ctx->pairkey[0].p);
   int e2 = T.mark();
   // --- tree rounds
   RET_IF(ensure(ctx, ctx->elem[0], ElemBuf<F>::bytes(ctx->h_totals[1] + 1)));

@@ -298,7 +298,9 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32
 // buckets, lanes stride over each bucket's pair range (replaces a second scattered 4-byte write per
 // entry in the scatter pass).
 static __global__ void __launch_bounds__(256) k_fill_pairkey(const uint32_t* __restrict__ po0, uint32_t NB,
-                                                            uint32_t P0, uint32_t* __restrict__ pairkey) {
+                                                            const unsigned long long* __restrict__ totals,
+                                                            uint32_t* __restrict__ pairkey) {
+  const uint32_t P0 = (uint32_t)totals[0];  // pair slots of round 0 (the host may not know it yet)
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t b0 = warp * 32;
