@@ -88,6 +88,9 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
     memset(tm, 0, sizeof *tm);
   }
   int rc;
+  ctx->pending.valid = false;
+  ctx->pending.window_bits = c;
+  ctx->pending.n_windows = 0;
   if (n == 0)
     rc = ops_of(ctx->curve)->zero_partial(ctx);
   else
@@ -257,13 +260,16 @@ int msm_b200_run(msm_b200_ctx* ctx, const void* scalars, size_t n, int scalar_la
     ctx->launches = 0;
     ctx->ev_used = 0;
   }
-  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, timing));
+  // the phase timings are resolved after the final synchronisation, so nothing waits in the middle of the call
+  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, on_device, form, window_bits, nullptr));
   Timer T(ctx);
   int d0 = T.mark();
   RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
   int d1 = T.mark();
   CK(cudaStreamSynchronize(ctx->stream));
   if (timing) {
+    memset(timing, 0, sizeof *timing);
+    RET_IF(resolve_timing(ctx, timing));
     timing->d2h_ms = T.ms(d0, d1);
     timing->kernel_launches = ctx->launches;
     timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();
@@ -282,9 +288,11 @@ int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, cons
   int i0 = T.mark();
   RET_IF(set_bases_impl(ctx, points, n, point_layout, 0, /*overlapped=*/true));
   int i1 = T.mark();
-  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, timing));
+  RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, nullptr));
   RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
   if (timing) {
+    memset(timing, 0, sizeof *timing);
+    RET_IF(resolve_timing(ctx, timing));
     timing->ingest_ms = T.ms(i0, i1);
     timing->kernel_launches = ctx->launches;
     timing->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - w0).count();

@@ -167,6 +167,8 @@ struct Timer {
 
 static int resolve_timing(msm_b200_ctx* ctx, msm_b200_timing* tm) {
   const PendingTiming& pt = ctx->pending;
+  tm->window_bits = pt.window_bits;
+  tm->n_windows = pt.n_windows;
   if (!pt.valid) return 0;  // nothing was launched (empty input, all-zero scalars, digit dump)
   CK(cudaStreamSynchronize(ctx->stream));
   Timer T(ctx);
@@ -342,6 +344,8 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   ctx->pending.valid = false;
   const int b = S::QBITS;  // Scalar.sizeInBits, src/msm-basic.ts:55
   const int K = (b + 1 + c - 1) / c;
+  ctx->pending.window_bits = c;
+  ctx->pending.n_windows = K;
   const uint32_t L = 1u << (c - 1);
   const size_t NB = (size_t)K * L;
   if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
@@ -471,6 +475,8 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   ctx->pending.valid = false;
   const int b = G::MAXBITS;  // Scalar.maxBits, src/wasm/glv.ts:216-226
   const int K = (b + 1 + c - 1) / c;
+  ctx->pending.window_bits = c;
+  ctx->pending.n_windows = K;
   const uint32_t L = 1u << (c - 1);
   const size_t NB = (size_t)K * L;
   const size_t S = 2 * n;
