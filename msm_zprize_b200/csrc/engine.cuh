@@ -266,8 +266,7 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
     LAUNCH(ctx, (k_tree_up<F, true, TREE_CTA>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top],
            (uint4*)ctx->lvl_pre[top].p, (uint4*)nullptr, (size_t)0);
   else
-    LAUNCH(ctx, (k_tree_up<F, true, TOP_CTA_MAX>), 1, TOP_CTA_MAX, (const uint4*)ctx->lvl_tot[top].p, M[top],
-           (uint4*)ctx->lvl_pre[top].p, (uint4*)nullptr, (size_t)0);
+    LAUNCH(ctx, k_tree_top2<F>, 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top], (uint4*)ctx->lvl_pre[top].p);
   if (two)
     LAUNCH(ctx, k_tree_down<F>, (unsigned)M[top], TREE_CTA, (uint4*)ctx->lvl_pre[ns].p, M[ns],
            (const uint4*)ctx->lvl_pre[top].p, M[top]);
