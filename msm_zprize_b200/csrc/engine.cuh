@@ -263,10 +263,11 @@ static int invert_totals(msm_b200_ctx* ctx, size_t M1) {
     LAUNCH(ctx, (k_tree_up<F, false, TREE_CTA>), (unsigned)M[top], TREE_CTA, (const uint4*)ctx->lvl_tot[ns].p, M[ns],
            (uint4*)ctx->lvl_pre[ns].p, (uint4*)ctx->lvl_tot[top].p, M[top]);
   if (M[top] <= (size_t)TREE_CTA)
-    LAUNCH(ctx, (k_tree_up<F, true, TREE_CTA>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top],
-           (uint4*)ctx->lvl_pre[top].p, (uint4*)nullptr, (size_t)0);
+    LAUNCH(ctx, (k_tree_top2<F, TREE_CTA / 2>), 1, TREE_CTA / 2, (const uint4*)ctx->lvl_tot[top].p, M[top],
+           (uint4*)ctx->lvl_pre[top].p);
   else
-    LAUNCH(ctx, k_tree_top2<F>, 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top], (uint4*)ctx->lvl_pre[top].p);
+    LAUNCH(ctx, (k_tree_top2<F, TREE_CTA>), 1, TREE_CTA, (const uint4*)ctx->lvl_tot[top].p, M[top],
+           (uint4*)ctx->lvl_pre[top].p);
   if (two)
     LAUNCH(ctx, k_tree_down<F>, (unsigned)M[top], TREE_CTA, (uint4*)ctx->lvl_pre[ns].p, M[ns],
            (const uint4*)ctx->lvl_pre[top].p, M[top]);

@@ -664,17 +664,17 @@ __global__ void __launch_bounds__(CTA) k_tree_up(const uint4* __restrict__ val, 
   if (i < M) st_soa<F>(others, M, i, o);
 }
 
-// Top of the product tree for up to 2 * TREE_CTA values: ONE block, two values per thread, so that the
-// shuffle scans run with 2 warps per SM sub-partition instead of 4 (the scans are bound by the IMAD pipe of
+// Top of the product tree for up to 2 * CTA values: ONE block, two values per thread, so that the
+// shuffle scans run with half as many warps per SM sub-partition (the scans are bound by the IMAD pipe of
 // the one SM they run on).  inverses[i] = 1 / val[i].
-template <class F>
-__global__ void __launch_bounds__(TREE_CTA) k_tree_top2(const uint4* __restrict__ val, size_t M, uint4* __restrict__ inverses) {
+template <class F, int CTA>
+__global__ void __launch_bounds__(CTA) k_tree_top2(const uint4* __restrict__ val, size_t M, uint4* __restrict__ inverses) {
   __shared__ uint32_t smem[97 * F::N + F::N];
   const size_t i0 = (size_t)threadIdx.x * 2;
   Fe<F> v0 = (i0 < M) ? ld_soa<F>(val, M, i0) : fe_one<F>();
   Fe<F> v1 = (i0 + 1 < M) ? ld_soa<F>(val, M, i0 + 1) : fe_one<F>();
   Fe<F> o, total;
-  block_products<F, TREE_CTA>(fe_mul(v0, v1), o, total, smem);
+  block_products<F, CTA>(fe_mul(v0, v1), o, total, smem);
   uint32_t* binv = smem + 97 * F::N;
   __syncthreads();
   if (threadIdx.x == 0) fe_to_smem<F>(binv, fe_inv(total));
