@@ -597,10 +597,13 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     if (((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)ctx->finish_max_elems &&
         (double)adds_left * (ctx->finish_add_modmuls - 6.0) <= (double)(R - r) * ctx->finish_round_modmuls) {
       RET_IF(ensure(ctx, ctx->buckets, NB * 3 * FE));
-      if (r == 0)
-        LAUNCH(ctx, (k_finish<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
-      else
-        LAUNCH(ctx, (k_finish<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+      if (r == 0) {
+        LAUNCH(ctx, (k_finish_slots<F, B3, true>), cdiv(P, 64), 64, a, (uint4*)ctx->buckets.p);
+        LAUNCH(ctx, (k_finish_rest<F, true>), cdiv(NB, 128), 128, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+      } else {
+        LAUNCH(ctx, (k_finish_slots<F, B3, false>), cdiv(P, 64), 64, a, (uint4*)ctx->buckets.p);
+        LAUNCH(ctx, (k_finish_rest<F, false>), cdiv(NB, 128), 128, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+      }
       finished_projective = true;
       break;
     }

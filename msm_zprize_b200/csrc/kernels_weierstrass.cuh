@@ -572,34 +572,49 @@ __global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_bwd(RoundArg
 }
 
 // Tail of the tree.  Once the additions that are left cost less as projective mixed additions than
-// as further latency-bound rounds (each round pays a product tree + one inversion), every bucket is
-// summed by one thread and ALL bucket sums are written out projective (no inversion): unfinished
-// buckets from their remaining elements, finished ones from `fin`, empty ones as the neutral
-// element.  The bucket reduction then reads this array instead of `fin`.
+// as further latency-bound rounds (each round pays a product tree + one inversion), every unfinished
+// bucket is summed by one thread and ALL bucket sums are written out projective (no inversion); the
+// bucket reduction then reads this array instead of `fin`.  Two kernels:
+//   k_finish_slots  one thread per PAIR SLOT of the round that would come next; the thread that owns a
+//                   bucket's first slot sums the bucket's elements.  Unfinished buckets are contiguous in
+//                   slot space, so the warps doing the mixed additions are densely populated (one thread
+//                   per bucket over all NB buckets leaves half the lanes of every warp idle);
+//   k_finish_rest   one thread per bucket for the cheap cases: empty -> neutral element, finished in an
+//                   earlier round -> copied from `fin`.
 template <class F, uint32_t B3, bool R0>
-__global__ void __launch_bounds__(64) k_finish(RoundArgs<F> a, uint32_t NB, uint4* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= NB) return;
-  uint4* o = buckets + (size_t)b * (3 * F::N / 4);
-  const uint32_t cnt = a.cnt[b];
-  uint32_t n = (uint32_t)(((unsigned long long)cnt + (1ull << a.r) - 1) >> a.r);
-  Proj<F> acc;
-  if (cnt == 0) {
-    acc = proj_zero<F>();
-  } else if (!R0 && n == 1) {
-    acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
-  } else {
-    size_t e0 = 2 * (size_t)a.po_r[b];
-    acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0));
+__global__ void __launch_bounds__(64) k_finish_slots(RoundArgs<F> a, uint4* __restrict__ buckets) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+  const uint32_t b = a.pairkey[i];
+  if ((uint32_t)i != a.po_r[b]) return;  // not the bucket's first slot
+  const uint32_t n = (uint32_t)(((unsigned long long)a.cnt[b] + (1ull << a.r) - 1) >> a.r);
+  const size_t e0 = 2 * i;
+  Proj<F> acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0));
 #pragma unroll 1
-    for (uint32_t j = 1; j < n; j++) {
-      Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
-      if (aff_is_inf(Q)) continue;
-      if constexpr (F::LAZY && B3 == 3) acc = proj_add_mixed_nr<F>(acc, Q);  // coordinates < 2p in registers
-      else acc = proj_add_mixed<F, B3>(acc, Q);
-    }
-    if constexpr (F::LAZY && B3 == 3) acc = proj_canon(acc);
+  for (uint32_t j = 1; j < n; j++) {
+    Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
+    if (aff_is_inf(Q)) continue;
+    if constexpr (F::LAZY && B3 == 3) acc = proj_add_mixed_nr<F>(acc, Q);  // coordinates < 2p in registers
+    else acc = proj_add_mixed<F, B3>(acc, Q);
   }
+  if constexpr (F::LAZY && B3 == 3) acc = proj_canon(acc);
+  uint4* o = buckets + (size_t)b * (3 * F::N / 4);
+  st_aos<F>(o, acc.X);
+  st_aos<F>(o + F::N / 4, acc.Y);
+  st_aos<F>(o + 2 * F::N / 4, acc.Z);
+}
+
+template <class F, bool R0>
+__global__ void __launch_bounds__(128) k_finish_rest(RoundArgs<F> a, uint32_t NB, uint4* __restrict__ buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  const uint32_t cnt = a.cnt[b];
+  const uint32_t n = (uint32_t)(((unsigned long long)cnt + (1ull << a.r) - 1) >> a.r);
+  Proj<F> acc;
+  if (cnt == 0) acc = proj_zero<F>();
+  else if (!R0 && n == 1) acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
+  else return;                                                 // has pair slots: k_finish_slots
+  uint4* o = buckets + (size_t)b * (3 * F::N / 4);
   st_aos<F>(o, acc.X);
   st_aos<F>(o + F::N / 4, acc.Y);
   st_aos<F>(o + 2 * F::N / 4, acc.Z);
