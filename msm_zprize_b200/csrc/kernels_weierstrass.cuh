@@ -446,6 +446,53 @@ __device__ __forceinline__ void block_products(const Fe<F>& v, Fe<F>& others, Fe
 }
 constexpr int BLOCK_PRODUCTS_SMEM_WORDS(int n) { return 97 * n; }
 
+// Same result with two thirds of the field products, for kernels in which EVERY resident warp runs this at the
+// same time (k_fwd in block mode: the scans are then bound by the IMAD pipe, not by latency): neighbouring
+// lanes multiply their values first, only NT / 2 threads (half of the warps) scan the pair products, and each
+// thread finishes with one product by its neighbour's value.  `stage`: NT / 2 field elements of shared memory.
+template <class F, int NT>
+__device__ __forceinline__ void block_products_paired(const Fe<F>& v, Fe<F>& others, Fe<F>& total, uint32_t* smem,
+                                                      uint32_t* stage) {
+  constexpr int NW = NT / 64;  // warps that scan
+  uint32_t* wtot = smem;
+  uint32_t* wpre = smem + 32 * F::N;
+  uint32_t* wsuf = smem + 64 * F::N;
+  uint32_t* btot = smem + 96 * F::N;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const Fe<F> partner = fe_shfl(v, lane ^ 1);
+  const Fe<F> pp = fe_mul(v, partner);
+  if (!(t & 1)) fe_to_smem<F>(stage + (t >> 1) * F::N, pp);
+  __syncthreads();
+  const bool active = t < NT / 2;  // whole warps
+  Fe<F> p, s;
+  if (active) {
+    warp_scan_products(fe_from_smem<F>(stage + t * F::N), lane, p, s);
+    if (lane == 31) fe_to_smem<F>(wtot + w * F::N, p);
+  }
+  __syncthreads();
+  if (w == 0) {
+    Fe<F> x = (lane < NW) ? fe_from_smem<F>(wtot + lane * F::N) : fe_one<F>(), xp, xs;
+    warp_scan_products(x, lane, xp, xs);
+    Fe<F> pre = fe_shfl_up(xp, 1), suf = fe_shfl_down(xs, 1);
+    if (lane == 0) pre = fe_one<F>();
+    if (lane == 31) suf = fe_one<F>();
+    fe_to_smem<F>(wpre + lane * F::N, pre);
+    fe_to_smem<F>(wsuf + lane * F::N, suf);
+    if (lane == 31) fe_to_smem<F>(btot, xp);
+  }
+  __syncthreads();
+  if (active) {
+    Fe<F> pe = fe_shfl_up(p, 1), se = fe_shfl_down(s, 1);
+    if (lane == 0) pe = fe_one<F>();
+    if (lane == 31) se = fe_one<F>();
+    Fe<F> o = fe_mul(fe_mul(fe_from_smem<F>(wpre + w * F::N), pe), fe_mul(se, fe_from_smem<F>(wsuf + w * F::N)));
+    fe_to_smem<F>(stage + t * F::N, o);  // product of all OTHER pairs, in place of this thread's own pair product
+  }
+  __syncthreads();
+  others = fe_mul(fe_from_smem<F>(stage + (t >> 1) * F::N), partner);
+  total = fe_from_smem<F>(btot);
+}
+
 // Loads of one pair.  Everything that depends only on the pair index (the two elements, or the two
 // sorted entries and then the gathered base points) is issued BEFORE the bucket lookups
 // (pairkey -> po_r / cnt), so a pair costs two dependent memory round trips instead of four.  The
@@ -512,6 +559,7 @@ __device__ __forceinline__ bool fwd_denominator(const RoundArgs<F>& a, size_t i,
 template <class F, bool R0, bool BLK>
 __global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_fwd(RoundArgs<F> a) {
   __shared__ uint32_t smem[BLK ? 97 * F::N : 1];
+  __shared__ uint32_t stage[BLK ? (ACC_THREADS / 2) * F::N : 1];
   const size_t chunk0 = (size_t)blockIdx.x * ((size_t)ACC_THREADS * a.B0);
   const size_t gid = (size_t)blockIdx.x * ACC_THREADS + threadIdx.x;
   Fe<F> run = fe_one<F>();
@@ -527,7 +575,7 @@ __global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_fwd(RoundArg
   }
   if (BLK) {
     Fe<F> others, total;
-    block_products<F, ACC_THREADS>(run, others, total, smem);
+    block_products_paired<F, ACC_THREADS>(run, others, total, smem, stage);
     st_soa<F>(a.tot, a.M1, gid, others);
     if (threadIdx.x == 0) st_soa<F>(a.blktot, gridDim.x, blockIdx.x, total);
   } else {
