@@ -25,11 +25,16 @@ __device__ __forceinline__ void quad_mul4(const Fe<F>& a0, const Fe<F>& b0, cons
                                           const Fe<F>& a2, const Fe<F>& b2, const Fe<F>& a3, const Fe<F>& b3,
                                           Fe<F>& p0, Fe<F>& p1, Fe<F>& p2, Fe<F>& p3) {
   const int lane = threadIdx.x & 31, q = lane & 3, base = lane & ~3;
+  // operand of this lane by bitwise selection (one 3-input logic op per step): ternaries on the lane number
+  // were compiled into divergent branches, ~24 reconvergence regions per doubling
+  const uint32_t m1 = 0u - (uint32_t)(q & 1), m2 = 0u - (uint32_t)((q >> 1) & 1);
   Fe<F> x, y;
 #pragma unroll
   for (int i = 0; i < F::N; i++) {
-    x.v[i] = q == 0 ? a0.v[i] : (q == 1 ? a1.v[i] : (q == 2 ? a2.v[i] : a3.v[i]));
-    y.v[i] = q == 0 ? b0.v[i] : (q == 1 ? b1.v[i] : (q == 2 ? b2.v[i] : b3.v[i]));
+    const uint32_t x01 = (a0.v[i] & ~m1) | (a1.v[i] & m1), x23 = (a2.v[i] & ~m1) | (a3.v[i] & m1);
+    const uint32_t y01 = (b0.v[i] & ~m1) | (b1.v[i] & m1), y23 = (b2.v[i] & ~m1) | (b3.v[i] & m1);
+    x.v[i] = (x01 & ~m2) | (x23 & m2);
+    y.v[i] = (y01 & ~m2) | (y23 & m2);
   }
   Fe<F> p = fe_mul_call(x, y);
 #pragma unroll
