@@ -170,7 +170,7 @@ int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, 
  * Field ops on the device, element-wise over `n` elements (32-bit limbs, internal Montgomery
  * form) -- the device side of the reference's per-op tests (src/field.test.ts:15-155).
  * field: 0 BLS12-377 Fq, 1 Pallas Fp, 2 BLS12-377 Fr, 3 BLS12-381 Fq.  op: 0 mul, 1 add, 2 sub, 3 inverse,
- * 4 square. */
+ * 4 square, 5 inverse by the quad-cooperative routine (csrc/inv_quad.cuh). */
 int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host,
                            const uint32_t* b_host, uint32_t* out_host, size_t n);
 /* GLV decomposition + signed digits on the device for `n` scalars (LE_BYTES): writes

@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include "engine.cuh"
 #include "microbench.cuh"
+#include "inv_quad.cuh"
 
 std::string& msm_global_err() {
   static thread_local std::string e;
@@ -122,17 +123,32 @@ static int combine_impl(msm_b200_ctx* ctx, const void* partials_dev, int count, 
 template <class F>
 __global__ void k_test_field(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fe<F> x, y, r;
-  for (int j = 0; j < F::N; j++) {
-    x.v[j] = a[i * F::N + j];
-    y.v[j] = b[i * F::N + j];
+  const bool valid = i < n;
+  Fe<F> x = fe_one<F>(), y = fe_one<F>(), r;
+  if (valid) {
+    for (int j = 0; j < F::N; j++) {
+      x.v[j] = a[i * F::N + j];
+      y.v[j] = b[i * F::N + j];
+    }
   }
-  if (op == 0) r = fe_mul(x, y);
+  if (op == 5) {
+    // quad-cooperative inverse: the whole warp works on one argument at a time
+    const int lane = threadIdx.x & 31;
+    r = x;
+    for (int src = 0; src < 32; src++) {
+      Fe<F> arg;
+      for (int j = 0; j < F::N; j++) arg.v[j] = __shfl_sync(0xffffffffu, x.v[j], src);
+      Fe<F> inv = fe_inv_quad(arg);
+      if (lane == src) r = inv;
+    }
+  } else if (!valid) {
+    return;
+  } else if (op == 0) r = fe_mul(x, y);
   else if (op == 1) r = fe_add(x, y);
   else if (op == 2) r = fe_sub(x, y);
   else if (op == 4) r = fe_sqr(x);
   else r = fe_inv(x);
+  if (!valid) return;
   for (int j = 0; j < F::N; j++) out[i * F::N + j] = r.v[j];
 }
 
@@ -361,7 +377,7 @@ int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t
 int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host, const uint32_t* b_host,
                            uint32_t* out_host, size_t n) {
   msm_b200_ctx* ctx = nullptr;
-  if (field < 0 || field > 3 || op < 0 || op > 4 || !a_host || !b_host || !out_host)
+  if (field < 0 || field > 3 || op < 0 || op > 5 || !a_host || !b_host || !out_host)
     return fail(nullptr, MSM_E_INVALID, "bad arguments");
   CK(cudaSetDevice(device));
   int N = (field == 0 || field == 3) ? 12 : 8;

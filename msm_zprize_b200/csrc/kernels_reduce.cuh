@@ -10,6 +10,7 @@
 // window whose X is the window sum; k_horner combines the windows (:310-321).
 #pragma once
 #include "kernels_common.cuh"
+#include "inv_quad.cuh"
 
 namespace msm {
 
@@ -193,11 +194,11 @@ struct WeierCurve {
     return R;
   }
   // canonical affine output words: x | y | is_zero
-  __device__ static void normalise(const Acc& a, uint32_t* out) {
-    Aff<F> A = proj_to_aff(a);
-    bool inf = aff_is_inf(A);
-    Fe<F> x = inf ? fe_zero<F>() : fe_from_mont(A.x);
-    Fe<F> y = inf ? fe_zero<F>() : fe_from_mont(A.y);
+  // `zi` = 1 / a.Z computed by the caller (quad-cooperative inversion, all lanes); a canonical
+  __device__ static void normalise(const Acc& a, const Fe<F>& zi, uint32_t* out) {
+    bool inf = fe_is_zero(a.Z);
+    Fe<F> x = inf ? fe_zero<F>() : fe_from_mont(fe_mul(a.X, zi));
+    Fe<F> y = inf ? fe_zero<F>() : fe_from_mont(fe_mul(a.Y, zi));
     for (int i = 0; i < F::N; i++) {
       out[i] = x.v[i];
       out[F::N + i] = y.v[i];
@@ -278,8 +279,7 @@ struct TeCurve {
     return R;
   }
   // (X/Z, Y/Z): src/bigint/twisted-edwards.ts:39-45; is_zero flags the neutral point (0, 1)
-  __device__ static void normalise(const Acc& a, uint32_t* out) {
-    Fe<F> zi = fe_inv(a.Z);
+  __device__ static void normalise(const Acc& a, const Fe<F>& zi, uint32_t* out) {
     Fe<F> x = fe_from_mont(fe_mul(a.X, zi));
     Fe<F> y = fe_from_mont(fe_mul(a.Y, zi));
     bool zero = fe_is_zero(x);
@@ -450,7 +450,9 @@ __global__ void k_finalize(const uint4* __restrict__ partials, int count, uint32
   typename C::Acc acc = C::ld(partials);
 #pragma unroll 1
   for (int i = 1; i < count; i++) acc = C::addq(acc, C::ld(partials + (size_t)i * (C::ACC_FE * C::F::N / 4)));
-  if (threadIdx.x == 0 && blockIdx.x == 0) C::normalise(C::canon(acc), out);
+  acc = C::canon(acc);
+  const Fe<typename C::F> zi = fe_inv_quad(acc.Z);  // every lane holds the same point: the warp inverts together
+  if (threadIdx.x == 0 && blockIdx.x == 0) C::normalise(acc, zi, out);
 }
 
 }  // namespace msm

@@ -13,6 +13,7 @@
 //                     as a multi-level product tree with one Fermat inversion per top element
 #pragma once
 #include "kernels_common.cuh"
+#include "inv_quad.cuh"
 
 namespace msm {
 
@@ -740,7 +741,10 @@ __global__ void __launch_bounds__(CTA) k_tree_top2(const uint4* __restrict__ val
   block_products<F, CTA>(fe_mul(v0, v1), o, total, smem);
   uint32_t* binv = smem + 97 * F::N;
   __syncthreads();
-  if (threadIdx.x == 0) fe_to_smem<F>(binv, fe_inv(total));
+  if (threadIdx.x < 32) {  // warp 0 inverts the grand total together (inv_quad.cuh)
+    const Fe<F> inv = fe_inv_quad(total);
+    if (threadIdx.x == 0) fe_to_smem<F>(binv, inv);
+  }
   __syncthreads();
   o = fe_mul(o, fe_from_smem<F>(binv));  // 1 / (v0 v1)
   if (i0 < M) st_soa<F>(inverses, M, i0, fe_mul(o, v1));

@@ -59,6 +59,10 @@ def test_field_ops_on_device(mz, field):
     assert _vals(test_field_op(0, field, 4, SQ, SQ)) == [x * x * Ri % p for x in sq]
     nz = [x if x else 1 for x in a][:64]
     assert _vals(test_field_op(0, field, 3, _limbs(nz, n), _limbs(nz, n))) == [pow(x, -1, p) * R * R % p for x in nz]
+    # the quad-cooperative inversion used at the top of the product tree (inv_quad.cuh); 200 values incl. edges,
+    # a count that is not a multiple of the warp size
+    nz2 = [x if x else 1 for x in a][:200] + [1, 2, p - 1, p - 2, (p - 1) // 2, R % p, 3]
+    assert _vals(test_field_op(0, field, 5, _limbs(nz2, n), _limbs(nz2, n))) == [pow(x, -1, p) * R * R % p for x in nz2]
 
 
 @pytest.mark.parametrize("name,params,c", [("bls12-377", O.BLS12_377, 13), ("pallas", O.PALLAS, 7),
