@@ -282,14 +282,14 @@ template <class C>
 static int zero_partial_t(msm_b200_ctx* ctx);
 
 // pair-slot offsets of `rounds` tree rounds (ctx->cnt -> ctx->po, ctx->totals)
-static int launch_scan(msm_b200_ctx* ctx, size_t NB, int rounds, uint32_t split = 0) {
+static int launch_scan(msm_b200_ctx* ctx, size_t NB, int rounds, uint32_t split = 0, int r0 = 0) {
   unsigned ntiles = cdiv(NB, SCAN_TILE);
-  RET_IF(ensure(ctx, ctx->tilesum, (size_t)rounds * ntiles * 4));
+  RET_IF(ensure(ctx, ctx->tilesum, (size_t)(MAX_ROUNDS + 1) * ntiles * 4));
   dim3 grid(ntiles, rounds);
   LAUNCH(ctx, k_scan_tiles, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (uint32_t*)ctx->tilesum.p, ntiles,
-         (unsigned long long*)ctx->totals.p, split);
+         (unsigned long long*)ctx->totals.p, split, r0);
   LAUNCH(ctx, k_scan_write, grid, SCAN_THREADS, (const uint32_t*)ctx->cnt.p, (uint32_t)NB, (const uint32_t*)ctx->tilesum.p,
-         ntiles, (uint32_t*)ctx->po.p, (unsigned long long*)ctx->totals.p, split);
+         ntiles, (uint32_t*)ctx->po.p, (unsigned long long*)ctx->totals.p, split, r0);
   CK(cudaGetLastError());
   return 0;
 }
@@ -512,7 +512,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   // --- offsets for every round; the host needs the totals (one sync), the scatter does not: it is queued
   //     first, sized by the upper bound 2 * P0 <= S * K + NB, so the GPU keeps working while the host wakes up
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
-  RET_IF(launch_scan(ctx, NB, MAX_ROUNDS + 1));
+  RET_IF(launch_scan(ctx, NB, SCAN_ROUNDS_FIRST));  // rounds 0 .. SCAN_ROUNDS_FIRST - 1; more below if a bucket is larger
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(ctx->totals_ready, ctx->stream));
   if (!digits_dump_dev) {
@@ -531,6 +531,12 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   int R = 1;
   while (((unsigned long long)1 << R) < maxcnt) R++;
   if (R > MAX_ROUNDS - 1) return fail(ctx, MSM_E_INVALID, "bucket too large");
+  if (R + 1 > SCAN_ROUNDS_FIRST && !digits_dump_dev) {  // large buckets: offsets of the remaining rounds
+    RET_IF(launch_scan(ctx, NB, R + 1 - SCAN_ROUNDS_FIRST, 0, SCAN_ROUNDS_FIRST));
+    CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->totals_ready, ctx->stream));
+    CK(cudaEventSynchronize(ctx->totals_ready));
+  }
   const size_t P0 = ctx->h_totals[0];
   if (digits_dump_dev) {  // tests only need the digits
     CK(cudaStreamSynchronize(ctx->stream));

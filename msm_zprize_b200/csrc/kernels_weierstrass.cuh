@@ -193,6 +193,8 @@ __global__ void k_hist_scatter(SortArgs a) {
 //   totals[MAX_ROUNDS+2] = sum of counts, totals[MAX_ROUNDS+3+r] = additions performed in round r.
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_THREADS * 4;
+constexpr int SCAN_ROUNDS_FIRST = 10;  // rounds scanned before the host knows the largest bucket (sizes up to 512);
+                                       // the rest only when needed
 
 // (`split` > 0, used by the generic bucket method: "round" 1 instead counts the virtual buckets
 //  ceil(cnt / split) that an oversized bucket is cut into.)
@@ -230,9 +232,10 @@ __device__ __forceinline__ uint32_t scan_block_exclusive(uint32_t local, uint32_
 
 static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ cnt, uint32_t NB,
                                                                    uint32_t* __restrict__ tilesum, uint32_t ntiles,
-                                                                   unsigned long long* __restrict__ totals, uint32_t split) {
+                                                                   unsigned long long* __restrict__ totals, uint32_t split,
+                                                                   int r0) {
   __shared__ uint32_t wsum[33];
-  const int r = blockIdx.y;
+  const int r = r0 + blockIdx.y;
   const uint32_t b0 = blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
   uint32_t local = 0, mx = 0;
   unsigned long long nent = 0, nadd = 0;
@@ -265,10 +268,11 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32
 static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_write(const uint32_t* __restrict__ cnt, uint32_t NB,
                                                                    const uint32_t* __restrict__ tilesum, uint32_t ntiles,
                                                                    uint32_t* __restrict__ po,
-                                                                   unsigned long long* __restrict__ totals, uint32_t split) {
+                                                                   unsigned long long* __restrict__ totals, uint32_t split,
+                                                                   int r0) {
   __shared__ uint32_t wsum[33];
   __shared__ unsigned long long sbase;
-  const int r = blockIdx.y;
+  const int r = r0 + blockIdx.y;
   // base = sum of the tile sums before this tile
   unsigned long long part = 0;
   for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) part += tilesum[(size_t)r * ntiles + i];
