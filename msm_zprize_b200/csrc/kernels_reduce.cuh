@@ -47,6 +47,27 @@ __device__ __forceinline__ void quad_mul4(const Fe<F>& a0, const Fe<F>& b0, cons
   }
 }
 
+// The product of this lane's (already selected) operands, then all four products of the quad to every lane
+template <class F>
+__device__ __forceinline__ void quad_mul_bcast(const Fe<F>& x, const Fe<F>& y, Fe<F>& p0, Fe<F>& p1, Fe<F>& p2, Fe<F>& p3) {
+  const int base = (threadIdx.x & 31) & ~3;
+  Fe<F> p = fe_mul_call(x, y);
+#pragma unroll
+  for (int i = 0; i < F::N; i++) {
+    p0.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 0);
+    p1.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 1);
+    p2.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 2);
+    p3.v[i] = __shfl_sync(0xffffffffu, p.v[i], base + 3);
+  }
+}
+template <class F>
+__device__ __forceinline__ Fe<F> fe_bitsel(uint32_t m, const Fe<F>& a, const Fe<F>& b) {  // m all ones: a, zero: b
+  Fe<F> r;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = (a.v[i] & m) | (b.v[i] & ~m);
+  return r;
+}
+
 // ---- curve-form traits ------------------------------------------------------------------
 template <class F_, uint32_t B3_>
 struct WeierCurve {
@@ -105,14 +126,19 @@ struct WeierCurve {
   // operations and every product below multiplies operands of at most 10p x 4p, 9p x 3p (< 152 p^2 / p).
   __device__ static Acc dbl_quad_lazy(const Acc& P) {
     Fe<F> t0, t1, t2, xy;
-    quad_mul4<F>(P.Y, P.Y, P.Y, P.Z, P.Z, P.Z, P.X, P.Y, t0, t1, t2, xy);  // inputs < 2p, outputs < p
+    // lane q multiplies (Y,Y) (Y,Z) (Z,Z) (X,Y): three selections per word instead of the generic six
+    const int q = threadIdx.x & 3;
+    const uint32_t m3 = 0u - (uint32_t)(q == 3), m2 = 0u - (uint32_t)(q == 2), m12 = 0u - (uint32_t)(q == 1 || q == 2);
+    quad_mul_bcast<F>(fe_bitsel(m3, P.X, fe_bitsel(m2, P.Z, P.Y)), fe_bitsel(m12, P.Z, P.Y), t0, t1, t2, xy);  // < p
     Fe<F> z3 = fe_shl_nr<F, 3>(t0);                      // 8 t0          < 8p
     Fe<F> t2b = fe_add_nr(fe_shl_nr<F, 1>(t2), t2);      // b3 t2 = 3 t2  < 3p
     Fe<F> y3 = fe_add_nr(t0, t2b);                       //               < 4p
     Fe<F> t23 = fe_add_nr(fe_shl_nr<F, 1>(t2b), t2b);    // 3 * (3 t2)    < 9p
     Fe<F> t0b = fe_sub_nr<F, 9>(t0, t23);                // t0 - t23 + 9p < 10p
     Fe<F> x3, zz, yy, xx;
-    quad_mul4<F>(z3, t2b, z3, t1, t0b, y3, t0b, xy, x3, zz, yy, xx);
+    // (z3,t2b) (z3,t1) (t0b,y3) (t0b,xy)
+    const uint32_t mhi = 0u - (uint32_t)(q >= 2), m1 = 0u - (uint32_t)(q & 1);
+    quad_mul_bcast<F>(fe_bitsel(mhi, t0b, z3), fe_bitsel(mhi, fe_bitsel(m1, xy, y3), fe_bitsel(m1, t1, t2b)), x3, zz, yy, xx);
     Acc R;
     R.X = fe_shl_nr<F, 1>(xx);   // < 2p
     R.Y = fe_add_nr(x3, yy);     // < 2p
