@@ -155,6 +155,10 @@ int msm_b200_combine(msm_b200_ctx* ctx, const void* partials_dev, int count, msm
  * scalars in LE_BYTES layout into device memory `dst_dev` (n * point_bytes / n * 32 bytes). */
 int msm_b200_random_points(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed);
 int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed);
+/* The same generators for a RANGE of a larger seeded set: element j of the output is element `first + j` of
+ * the set that msm_b200_random_points / _scalars(seed) define -- each GPU generates its own shard. */
+int msm_b200_random_points_at(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed);
+int msm_b200_random_scalars_at(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed);
 size_t msm_b200_point_bytes(const msm_b200_ctx* ctx, int layout);
 size_t msm_b200_scalar_bytes(const msm_b200_ctx* ctx, int layout);
 
@@ -166,26 +170,42 @@ int msm_b200_host_free_pinned(void* host);
 int msm_b200_memcpy_d2h(msm_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 
-/* -- test / measurement hooks ----------------------------------------------------------------
- * Field ops on the device, element-wise over `n` elements (32-bit limbs, internal Montgomery
- * form) -- the device side of the reference's per-op tests (src/field.test.ts:15-155).
- * field: 0 BLS12-377 Fq, 1 Pallas Fp, 2 BLS12-377 Fr, 3 BLS12-381 Fq.  op: 0 mul, 1 add, 2 sub, 3 inverse,
- * 4 square, 5 inverse by the quad-cooperative routine (csrc/inv_quad.cuh). */
-int msm_b200_test_field_op(int device, int field, int op, const uint32_t* a_host,
-                           const uint32_t* b_host, uint32_t* out_host, size_t n);
-/* GLV decomposition + signed digits on the device for `n` scalars (LE_BYTES): writes
- * 2n * K digits as u32 (bucket l | sign << 31), half-scalar major.  (src/glv/glv-test.ts,
- * src/msm-batched-affine.ts:172-200) */
-int msm_b200_test_digits(msm_b200_ctx* ctx, const void* scalars_host, size_t n, int window_bits,
-                         uint32_t* digits_host, int* n_windows);
-/* Integer-pipe micro-benchmarks (the measured roofline denominators): which = 0 IMAD (mad.lo),
- * 1 IMAD.WIDE (mad.wide.u32), 2 IMAD.WIDE with carry in/out (mad.lo.cc/madc.hi.cc chains),
- * 5 IMAD.HI, 8 IADD3, 3 Montgomery product 12 limbs, 4 Montgomery product 8 limbs,
- * 6 / 7 Montgomery squaring 12 / 8 limbs; 9 / 10 / 11 latency of a chain of projective doublings in ONE warp
- * (quad-cooperative 12 limbs / one lane 12 limbs / quad-cooperative 8 limbs: what bounds the Horner tail).
- * Returns operations per second (limb products for 0-2 and 5, adds for 8, modmuls for 3-4 and 6-7,
- * doublings for 9-11). */
-int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, float* ms);
+/* -- several GPUs behind ONE call ------------------------------------------------------------
+ * The reference's msm is one call that fans out internally: every pool thread takes a static range of the
+ * points (range(), src/threads/threads.ts:354-359) and the main thread adds the partition sums
+ * (src/msm-batched-affine.ts:294-322).  msm_b200_multi_* is that shape over the GPUs of one box: the point set
+ * shards by contiguous range (device g owns [g * per, (g + 1) * per), per = ceil(n / n_dev)), one host thread per
+ * device inside the library drives the complete single-GPU pipeline on its range, the n_dev partial points
+ * (<= 144 bytes each) are gathered with one ncclAllGather over NVLink (libnccl.so.2 opened at run time; peer
+ * copies when it is absent or MSM_B200_GATHER=peer) and device 0 adds them and normalises.  The result is
+ * identical to the single-GPU one for every n_dev.  A multi context is single-caller like msm_b200_ctx (calls
+ * are serialised by an internal mutex). */
+typedef struct msm_b200_multi msm_b200_multi;
+int msm_b200_multi_create(msm_b200_multi** out, int curve, const int* devices, int n_dev);
+void msm_b200_multi_destroy(msm_b200_multi* m);
+const char* msm_b200_multi_last_error(const msm_b200_multi* m);
+int msm_b200_multi_devices(const msm_b200_multi* m);
+/* "ncclAllGather (NCCL <version>, ncclCommInitAll)" | "peer copies (cudaMemcpyPeerAsync)" | "none (single device)" */
+const char* msm_b200_multi_gather_kind(const msm_b200_multi* m);
+/* the per-device context i (generators, device memory helpers); owned by `m` */
+msm_b200_ctx* msm_b200_multi_ctx(msm_b200_multi* m, int i);
+/* msm_b200_set_bases over all devices: host points, range-sharded by the library */
+int msm_b200_multi_set_bases(msm_b200_multi* m, const void* points_host, size_t n, int layout);
+/* bases already resident on the devices: shard i = n_per_dev[i] points at points_dev[i] in device i's memory
+ * (global order: shard 0, shard 1, ...) */
+int msm_b200_multi_set_bases_sharded(msm_b200_multi* m, const void* const* points_dev, const size_t* n_per_dev, int layout);
+/* msm_b200_run over all devices: host scalars (n <= resident bases; the first n points of the global order) */
+int msm_b200_multi_run(msm_b200_multi* m, const void* scalars_host, size_t n, int scalar_layout, int form, int window_bits,
+                       msm_b200_point* out, msm_b200_timing* timing);
+/* the same with the scalars already on the devices, one shard per device matching the resident bases */
+int msm_b200_multi_run_sharded(msm_b200_multi* m, const void* const* scalars_dev, int scalar_layout, int form, int window_bits,
+                               msm_b200_point* out, msm_b200_timing* timing);
+/* msm_b200_msm over all devices (one-shot: points and scalars from the host every call) */
+int msm_b200_multi_msm(msm_b200_multi* m, const void* scalars_host, int scalar_layout, const void* points_host, int point_layout,
+                       size_t n, int form, int window_bits, msm_b200_point* out, msm_b200_timing* timing);
+/* `timing` of the calls above = the slowest device's phases (launches and additions summed, total_ms = the
+ * call's host clock); this returns every device's own phases of the last call */
+int msm_b200_multi_last_timings(msm_b200_multi* m, msm_b200_timing* per_device, int count);
 
 #ifdef __cplusplus
 }

@@ -49,10 +49,15 @@ EXPORTS = [
     "msm_b200_set_bases", "msm_b200_set_bases_async", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial", "msm_b200_last_timing",
     "msm_b200_partial_bytes", "msm_b200_combine", "msm_b200_random_points",
     "msm_b200_random_scalars", "msm_b200_point_bytes", "msm_b200_scalar_bytes",
+    "msm_b200_random_points_at", "msm_b200_random_scalars_at",
     "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
     "msm_b200_host_free_pinned", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
-    "msm_b200_test_field_op", "msm_b200_test_digits", "msm_b200_microbench",
+    "msm_b200_multi_create", "msm_b200_multi_destroy", "msm_b200_multi_last_error", "msm_b200_multi_devices",
+    "msm_b200_multi_gather_kind", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_set_bases_sharded",
+    "msm_b200_multi_run", "msm_b200_multi_run_sharded", "msm_b200_multi_msm", "msm_b200_multi_last_timings",
 ]
+# include/msm_b200_test.h
+TEST_EXPORTS = ["msm_b200_test_field_op", "msm_b200_test_digits", "msm_b200_microbench"]
 
 
 def lib() -> C.CDLL:
@@ -81,6 +86,8 @@ def lib() -> C.CDLL:
     L.msm_b200_combine.argtypes = [vp, vp, ci, C.POINTER(Point)]
     L.msm_b200_random_points.argtypes = [vp, vp, sz, C.c_uint64]
     L.msm_b200_random_scalars.argtypes = [vp, vp, sz, C.c_uint64]
+    L.msm_b200_random_points_at.argtypes = [vp, vp, sz, sz, C.c_uint64]
+    L.msm_b200_random_scalars_at.argtypes = [vp, vp, sz, sz, C.c_uint64]
     L.msm_b200_point_bytes.argtypes = [vp, ci]
     L.msm_b200_point_bytes.restype = sz
     L.msm_b200_scalar_bytes.argtypes = [vp, ci]
@@ -91,6 +98,22 @@ def lib() -> C.CDLL:
     L.msm_b200_host_free_pinned.argtypes = [vp]
     L.msm_b200_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.msm_b200_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.msm_b200_multi_create.argtypes = [C.POINTER(vp), ci, C.POINTER(ci), ci]
+    L.msm_b200_multi_destroy.argtypes = [vp]
+    L.msm_b200_multi_destroy.restype = None
+    L.msm_b200_multi_last_error.argtypes = [vp]
+    L.msm_b200_multi_last_error.restype = C.c_char_p
+    L.msm_b200_multi_devices.argtypes = [vp]
+    L.msm_b200_multi_gather_kind.argtypes = [vp]
+    L.msm_b200_multi_gather_kind.restype = C.c_char_p
+    L.msm_b200_multi_ctx.argtypes = [vp, ci]
+    L.msm_b200_multi_ctx.restype = vp
+    L.msm_b200_multi_set_bases.argtypes = [vp, vp, sz, ci]
+    L.msm_b200_multi_set_bases_sharded.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), ci]
+    L.msm_b200_multi_run.argtypes = [vp, vp, sz, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
+    L.msm_b200_multi_run_sharded.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
+    L.msm_b200_multi_msm.argtypes = [vp, vp, ci, vp, ci, sz, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
+    L.msm_b200_multi_last_timings.argtypes = [vp, C.POINTER(Timing), ci]
     L.msm_b200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
     L.msm_b200_test_digits.argtypes = [vp, vp, sz, ci, vp, C.POINTER(ci)]
     L.msm_b200_microbench.argtypes = [ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_float)]
@@ -98,9 +121,12 @@ def lib() -> C.CDLL:
     return L
 
 
-def check(rc: int, ctx=None):
+def check(rc: int, ctx=None, multi=None):
     if rc == 0:
         return
     L = lib()
-    msg = (L.msm_b200_last_error(ctx) if ctx else L.msm_b200_global_error()) or b""
+    if multi:
+        msg = L.msm_b200_multi_last_error(multi) or b""
+    else:
+        msg = (L.msm_b200_last_error(ctx) if ctx else L.msm_b200_global_error()) or b""
     raise MsmError(rc, msg.decode("utf-8", "replace"))

@@ -1,5 +1,7 @@
 // libmsm_b200.so -- the C ABI (include/msm_b200.h) over the per-curve engines.
 #include <cstdlib>
+#include <algorithm>
+#include "../../include/msm_b200_test.h"
 #include "engine.cuh"
 #include "microbench.cuh"
 #include "inv_quad.cuh"
@@ -171,13 +173,15 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   ctx->device = device;
   ctx->curve = curve;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (const char* e = getenv("MSM_B200_FINISH_ADD")) ctx->finish_add_modmuls = atof(e);
-  if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = atof(e);
-  if (const char* e = getenv("MSM_B200_FINISH_ELEMS")) ctx->finish_max_elems = atoi(e);
-  if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = atoi(e);
-  if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = atoi(e);
-  if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = atoi(e);
-  if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)atoll(e);
+  // development knobs (launch shapes only, never results); out-of-range values are clamped to what the
+  // kernels support: group bits 1..5 (a group must fit a warp), at least one pair / element
+  if (const char* e = getenv("MSM_B200_FINISH_ADD")) ctx->finish_add_modmuls = std::max(6.0, atof(e));
+  if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = std::max(0.0, atof(e));
+  if (const char* e = getenv("MSM_B200_FINISH_ELEMS")) ctx->finish_max_elems = std::max(1, atoi(e));
+  if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = std::min(std::max(1, atoi(e)), (int)ACC_MAX_PAIRS);
+  if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = std::min(std::max(1, atoi(e)), 5);
+  if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = std::min(std::max(1, atoi(e)), 5);
+  if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)std::max(1ll, atoll(e));
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {
@@ -301,9 +305,10 @@ int msm_b200_msm(msm_b200_ctx* ctx, const void* scalars, int scalar_layout, cons
   ctx->launches = 0;
   ctx->ev_used = 0;
   Timer T(ctx);
-  int i0 = T.mark();
+  // upload + ingest run on the copy stream (overlapped with the scalar phases): time them there
+  int i0 = T.mark(ctx->copy_stream);
   RET_IF(set_bases_impl(ctx, points, n, point_layout, 0, /*overlapped=*/true));
-  int i1 = T.mark();
+  int i1 = T.mark(ctx->copy_stream);
   RET_IF(run_partial_impl(ctx, scalars, n, scalar_layout, 0, form, window_bits, nullptr));
   RET_IF(combine_impl(ctx, ctx->partial.p, 1, out));
   if (timing) {
@@ -361,16 +366,22 @@ int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, 
   return 0;
 }
 
-int msm_b200_random_points(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+int msm_b200_random_points_at(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed) {
   if (!ctx || !dst_dev) return fail(ctx, MSM_E_INVALID, "bad arguments");
   CK(cudaSetDevice(ctx->device));
-  return ops_of(ctx->curve)->random_points(ctx, dst_dev, n, seed);
+  return ops_of(ctx->curve)->random_points(ctx, dst_dev, first, n, seed);
+}
+int msm_b200_random_points(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  return msm_b200_random_points_at(ctx, dst_dev, 0, n, seed);
 }
 
-int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+int msm_b200_random_scalars_at(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed) {
   if (!ctx || !dst_dev) return fail(ctx, MSM_E_INVALID, "bad arguments");
   CK(cudaSetDevice(ctx->device));
-  return ops_of(ctx->curve)->random_scalars(ctx, dst_dev, n, seed);
+  return ops_of(ctx->curve)->random_scalars(ctx, dst_dev, first, n, seed);
+}
+int msm_b200_random_scalars(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+  return msm_b200_random_scalars_at(ctx, dst_dev, 0, n, seed);
 }
 
 // ---- test / measurement hooks ----
@@ -475,3 +486,5 @@ int msm_b200_microbench(int device, int which, int iters, double* ops_per_sec, f
 }
 
 }  // extern "C"
+
+#include "multi.cuh"

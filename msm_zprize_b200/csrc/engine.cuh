@@ -148,14 +148,14 @@ static int ceil_log2_sz(size_t n) {
 struct Timer {
   msm_b200_ctx* ctx;
   explicit Timer(msm_b200_ctx* c) : ctx(c) {}
-  int mark() {  // records an event on the context's stream, returns its index
+  int mark(cudaStream_t on = nullptr) {  // records an event on the context's stream (or `on`), returns its index
     std::vector<cudaEvent_t>& ev = ctx->ev;
     if (ctx->ev_used == ev.size()) {
       cudaEvent_t e;
       cudaEventCreate(&e);
       ev.push_back(e);
     }
-    cudaEventRecord(ev[ctx->ev_used], ctx->stream);
+    cudaEventRecord(ev[ctx->ev_used], on ? on : ctx->stream);
     return (int)ctx->ev_used++;
   }
   float ms(int a, int b) {
@@ -451,14 +451,14 @@ static int finalize_any(msm_b200_ctx* ctx, const void* partials_dev, int count, 
 }
 
 template <class C, class S>
-static int random_points_t(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
+static int random_points_t(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed) {
   using F = typename C::F;
   size_t entries = (size_t)RP_TABLES << RP_BITS;
   RET_IF(ensure(ctx, ctx->rp_tables, entries * 2 * F::N * 4));
   LAUNCH(ctx, k_rp_tables<C>, cdiv(entries, 64), 64, (uint4*)ctx->rp_tables.p, seed);
   size_t threads = (n + RP_BATCH - 1) / RP_BATCH;
   LAUNCH(ctx, k_rp_points<C>, cdiv(threads, 64), 64, (const uint4*)ctx->rp_tables.p, (uint8_t*)dst_dev, n,
-         seed ^ 0x5EEDull);
+         seed ^ 0x5EEDull, first);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -708,8 +708,8 @@ struct CurveOps {
              uint32_t* digits_dump_dev);
   int (*zero_partial)(msm_b200_ctx*);
   int (*finalize)(msm_b200_ctx*, const void* partials_dev, int count, msm_b200_point* out);
-  int (*random_points)(msm_b200_ctx*, void* dst_dev, size_t n, uint64_t seed);
-  int (*random_scalars)(msm_b200_ctx*, void* dst_dev, size_t n, uint64_t seed);
+  int (*random_points)(msm_b200_ctx*, void* dst_dev, size_t first, size_t n, uint64_t seed);
+  int (*random_scalars)(msm_b200_ctx*, void* dst_dev, size_t first, size_t n, uint64_t seed);
 };
 const CurveOps* curve_ops_bls377();
 const CurveOps* curve_ops_pallas();
@@ -725,8 +725,8 @@ static int zero_partial_t(msm_b200_ctx* ctx) {
 }
 
 template <class S>
-static int random_scalars_t(msm_b200_ctx* ctx, void* dst_dev, size_t n, uint64_t seed) {
-  LAUNCH(ctx, k_random_scalars<S>, cdiv(n, 256), 256, (uint32_t*)dst_dev, n, seed);
+static int random_scalars_t(msm_b200_ctx* ctx, void* dst_dev, size_t first, size_t n, uint64_t seed) {
+  LAUNCH(ctx, k_random_scalars<S>, cdiv(n, 256), 256, (uint32_t*)dst_dev, n, seed, first);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -160,10 +160,10 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
 // sampling -- the distribution of src/curve-random.ts:151-194.  Stream i starts at
 // seed + (i+1) * 0xD1342543DE82EF95.
 template <class S>
-__global__ void k_random_scalars(uint32_t* __restrict__ out, size_t n, uint64_t seed) {
+__global__ void k_random_scalars(uint32_t* __restrict__ out, size_t n, uint64_t seed, size_t first) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t st = seed + (uint64_t)(i + 1) * 0xD1342543DE82EF95ull;
+  uint64_t st = seed + (uint64_t)(first + i + 1) * 0xD1342543DE82EF95ull;  // `first`: global index of out[0]
   uint32_t s[8];
   for (;;) {
     for (int j = 0; j < 4; j++) {
@@ -242,7 +242,8 @@ constexpr int RP_BATCH = 8;
 
 // Each thread produces RP_BATCH points (one shared inversion), canonical little-endian x | y.
 template <class C>
-__global__ void k_rp_points(const uint4* __restrict__ tables, uint8_t* __restrict__ out, size_t n, uint64_t seed) {
+__global__ void k_rp_points(const uint4* __restrict__ tables, uint8_t* __restrict__ out, size_t n, uint64_t seed,
+                            size_t first) {
   using F = typename C::F;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i0 = t * RP_BATCH;
@@ -253,7 +254,7 @@ __global__ void k_rp_points(const uint4* __restrict__ tables, uint8_t* __restric
   int m = (int)((n - i0 < (size_t)RP_BATCH) ? (n - i0) : RP_BATCH);
 #pragma unroll 1
   for (int u = 0; u < m; u++) {
-    uint64_t st = seed + (uint64_t)(i0 + u + 1) * 0xD1342543DE82EF95ull;
+    uint64_t st = seed + (uint64_t)(first + i0 + u + 1) * 0xD1342543DE82EF95ull;  // `first`: global index of out[0]
     uint64_t r = splitmix64(st);
     typename C::Acc acc = C::zero();
 #pragma unroll 1

@@ -28,15 +28,18 @@ class MsmResult:
     timing: dict
 
 
-def _as_buffer(a) -> Tuple[C.c_void_p, object]:
-    """Returns (pointer, keepalive) for bytes / bytearray / numpy input without copying numpy."""
+def _as_buffer(a, need: int = 0, what: str = "buffer") -> Tuple[C.c_void_p, object]:
+    """Returns (pointer, keepalive) for bytes / bytearray / numpy input without copying numpy.  A buffer
+    shorter than `need` bytes is refused here (MSM_E_INVALID) instead of being read past its end by the copy."""
     if isinstance(a, np.ndarray):
-        a = np.ascontiguousarray(a)
-        return C.c_void_p(a.ctypes.data), a
-    if isinstance(a, (bytes, bytearray, memoryview)):
+        arr = np.ascontiguousarray(a)
+    elif isinstance(a, (bytes, bytearray, memoryview)):
         arr = np.frombuffer(a, dtype=np.uint8)
-        return C.c_void_p(arr.ctypes.data), arr
-    raise TypeError(f"unsupported buffer type {type(a)}")
+    else:
+        raise TypeError(f"unsupported buffer type {type(a)}")
+    if arr.nbytes < need:
+        raise L.MsmError(L.E_INVALID, f"{what} holds {arr.nbytes} bytes, the call needs {need}")
+    return C.c_void_p(arr.ctypes.data), arr
 
 
 class PinnedBuffer:
@@ -50,6 +53,7 @@ class PinnedBuffer:
 
     def free(self):
         if self.ptr:
+            self.array = None  # the view must not outlive the memory
             L.lib().msm_b200_host_free_pinned(self.ptr)
             self.ptr = C.c_void_p()
 
@@ -100,13 +104,13 @@ class MsmEngine:
 
     # -- inputs
     def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
-        ptr, keep = _as_buffer(points)
+        ptr, keep = _as_buffer(points, n * self.point_bytes(layout), "point buffer")
         L.check(self._lib.msm_b200_set_bases(self._ctx, ptr, n, layout, 0), self._ctx)
 
     def set_bases_async(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
         """Queues upload + ingest on the copy stream; the next run()/run_partial() waits for it where it first
         reads a base point.  `points` must stay alive and unchanged until that run has returned."""
-        ptr, keep = _as_buffer(points)
+        ptr, keep = _as_buffer(points, n * self.point_bytes(layout), "point buffer")
         self._pending_points = keep
         L.check(self._lib.msm_b200_set_bases_async(self._ctx, ptr, n, layout), self._ctx)
 
@@ -125,7 +129,7 @@ class MsmEngine:
         if on_device:
             ptr, keep = C.c_void_p(int(scalars)), None
         else:
-            ptr, keep = _as_buffer(scalars)
+            ptr, keep = _as_buffer(scalars, n * self.scalar_bytes(layout), "scalar buffer")
         form = self.default_form if form is None else form
         L.check(self._lib.msm_b200_run(self._ctx, ptr, n, layout, int(on_device), form, window_bits,
                                        C.byref(pt), C.byref(tm)), self._ctx)
@@ -134,8 +138,8 @@ class MsmEngine:
     def msm(self, scalars, points, n: int, scalar_layout: int = L.LAYOUT_LE_BYTES,
             point_layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None, window_bits: int = 0) -> MsmResult:
         pt, tm = L.Point(), L.Timing()
-        sp, k1 = _as_buffer(scalars)
-        pp, k2 = _as_buffer(points)
+        sp, k1 = _as_buffer(scalars, n * self.scalar_bytes(scalar_layout), "scalar buffer")
+        pp, k2 = _as_buffer(points, n * self.point_bytes(point_layout), "point buffer")
         form = self.default_form if form is None else form
         L.check(self._lib.msm_b200_msm(self._ctx, sp, scalar_layout, pp, point_layout, n, form, window_bits,
                                        C.byref(pt), C.byref(tm)), self._ctx)
@@ -150,7 +154,7 @@ class MsmEngine:
         if on_device:
             ptr, keep = C.c_void_p(int(scalars)), None
         else:
-            ptr, keep = _as_buffer(scalars)
+            ptr, keep = _as_buffer(scalars, n * self.scalar_bytes(layout), "scalar buffer")
         form = self.default_form if form is None else form
         L.check(self._lib.msm_b200_run_partial(self._ctx, ptr, n, layout, int(on_device), form, window_bits,
                                                C.c_void_p(partial_dev_ptr), C.byref(tm) if timing else None),
@@ -186,11 +190,12 @@ class MsmEngine:
         ptr, keep = _as_buffer(host)
         L.check(self._lib.msm_b200_memcpy_h2d(self._ctx, C.c_void_p(dev_ptr), ptr, keep.nbytes), self._ctx)
 
-    def random_points_device(self, dev_ptr: int, n: int, seed: int):
-        L.check(self._lib.msm_b200_random_points(self._ctx, C.c_void_p(dev_ptr), n, seed), self._ctx)
+    def random_points_device(self, dev_ptr: int, n: int, seed: int, first: int = 0):
+        """`first`: global index of the first point (a shard of the larger seeded set)."""
+        L.check(self._lib.msm_b200_random_points_at(self._ctx, C.c_void_p(dev_ptr), first, n, seed), self._ctx)
 
-    def random_scalars_device(self, dev_ptr: int, n: int, seed: int):
-        L.check(self._lib.msm_b200_random_scalars(self._ctx, C.c_void_p(dev_ptr), n, seed), self._ctx)
+    def random_scalars_device(self, dev_ptr: int, n: int, seed: int, first: int = 0):
+        L.check(self._lib.msm_b200_random_scalars_at(self._ctx, C.c_void_p(dev_ptr), first, n, seed), self._ctx)
 
     # -- test hooks
     def test_digits(self, scalars_le: bytes, n: int, window_bits: int) -> np.ndarray:
@@ -201,6 +206,97 @@ class MsmEngine:
         L.check(self._lib.msm_b200_test_digits(self._ctx, ptr, n, window_bits, C.c_void_p(out.ctypes.data),
                                                C.byref(K)), self._ctx)
         return out[: 2 * n * K.value].reshape(2 * n, K.value)
+
+
+class MultiMsmEngine:
+    """Several GPUs behind one call (msm_b200_multi_*): the library shards the points by range, drives every
+    device from its own host thread, gathers the partial points (NCCL / peer copies) and adds them on
+    device 0.  No torch, no torchrun: this is what the N-API addon calls with `devices[]`."""
+
+    def __init__(self, curve: str | int, devices):
+        self.curve = CURVES[curve] if isinstance(curve, str) else int(curve)
+        self.devices = list(devices)
+        self._lib = L.lib()
+        self._m = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        L.check(self._lib.msm_b200_multi_create(C.byref(self._m), self.curve, arr, len(self.devices)))
+        self.field_bytes = FIELD_BYTES[self.curve]
+        self.default_form = L.FORM_TE_EXTENDED if self.curve == L.CURVE_ED_ON_BLS12_377 else L.FORM_AFFINE_GLV
+        self.gather_kind = (self._lib.msm_b200_multi_gather_kind(self._m) or b"").decode()
+        # per-device views (generators, device memory); owned by the multi context
+        self.shards = []
+        for i in range(len(self.devices)):
+            e = MsmEngine.__new__(MsmEngine)
+            e.curve, e.device, e._lib = self.curve, self.devices[i], self._lib
+            e._ctx = C.c_void_p(self._lib.msm_b200_multi_ctx(self._m, i))
+            e.field_bytes, e.default_form = self.field_bytes, self.default_form
+            e.close = lambda: None  # not ours to destroy
+            self.shards.append(e)
+
+    def close(self):
+        if self._m:
+            for e in self.shards:
+                e._ctx = C.c_void_p()
+            self._lib.msm_b200_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _result(self, pt, tm):
+        return MsmResult(int.from_bytes(bytes(pt.x), "little"), int.from_bytes(bytes(pt.y), "little"), bool(pt.is_zero),
+                         tm.as_dict())
+
+    def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
+        ptr, keep = _as_buffer(points, n * self.shards[0].point_bytes(layout), "point buffer")
+        L.check(self._lib.msm_b200_multi_set_bases(self._m, ptr, n, layout), multi=self._m)
+
+    def set_bases_sharded(self, dev_ptrs, counts, layout: int = L.LAYOUT_LE_BYTES):
+        p = (C.c_void_p * len(dev_ptrs))(*[C.c_void_p(int(x)) for x in dev_ptrs])
+        c = (C.c_size_t * len(counts))(*counts)
+        L.check(self._lib.msm_b200_multi_set_bases_sharded(self._m, p, c, layout), multi=self._m)
+
+    def run(self, scalars, n: int, layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None,
+            window_bits: int = 0) -> MsmResult:
+        pt, tm = L.Point(), L.Timing()
+        ptr, keep = _as_buffer(scalars, n * self.shards[0].scalar_bytes(layout), "scalar buffer")
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_multi_run(self._m, ptr, n, layout, form, window_bits, C.byref(pt), C.byref(tm)),
+                multi=self._m)
+        return self._result(pt, tm)
+
+    def run_sharded(self, dev_ptrs, layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None,
+                    window_bits: int = 0) -> MsmResult:
+        pt, tm = L.Point(), L.Timing()
+        p = (C.c_void_p * len(dev_ptrs))(*[C.c_void_p(int(x)) for x in dev_ptrs])
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_multi_run_sharded(self._m, p, layout, form, window_bits, C.byref(pt), C.byref(tm)),
+                multi=self._m)
+        return self._result(pt, tm)
+
+    def msm(self, scalars, points, n: int, scalar_layout: int = L.LAYOUT_LE_BYTES, point_layout: int = L.LAYOUT_LE_BYTES,
+            form: Optional[int] = None, window_bits: int = 0) -> MsmResult:
+        pt, tm = L.Point(), L.Timing()
+        sp, k1 = _as_buffer(scalars, n * self.shards[0].scalar_bytes(scalar_layout), "scalar buffer")
+        pp, k2 = _as_buffer(points, n * self.shards[0].point_bytes(point_layout), "point buffer")
+        form = self.default_form if form is None else form
+        L.check(self._lib.msm_b200_multi_msm(self._m, sp, scalar_layout, pp, point_layout, n, form, window_bits,
+                                             C.byref(pt), C.byref(tm)), multi=self._m)
+        return self._result(pt, tm)
+
+    def last_timings(self):
+        arr = (L.Timing * len(self.devices))()
+        L.check(self._lib.msm_b200_multi_last_timings(self._m, arr, len(self.devices)), multi=self._m)
+        return [t.as_dict() for t in arr]
 
 
 def test_field_op(device: int, field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -9,28 +9,41 @@ function names and argument meaning over the CUDA engine, so that tests read lik
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+import itertools
+from dataclasses import dataclass, field
 from typing import Optional
 
 from . import _lib as L
 from .engine import MsmEngine
 
 
+_uids = itertools.count(1)
+
+
 @dataclass
 class DeviceBuffer:
     """What a wasm-memory pointer is in the reference: a handle to inputs that already live where the
-    MSM runs.  `layout` is LE_BYTES for generated / converted data."""
+    MSM runs.  `layout` is LE_BYTES for generated / converted data.
+
+    `uid` is unique per allocation and `version` counts the writes into it: the resident-bases cache of
+    `Parallel` is keyed on both, never on the address (cudaMalloc hands a freed address out again, and a
+    buffer can be regenerated in place)."""
     ptr: int
     n: int
     layout: int = L.LAYOUT_LE_BYTES
+    uid: int = field(default_factory=lambda: next(_uids))
+    version: int = 0
+
+    def touch(self):
+        """call after writing new contents through `ptr` by other means than this module"""
+        self.version += 1
 
 
 class Parallel:
     def __init__(self, engine: MsmEngine, twisted_edwards: bool):
         self.engine = engine
         self.te = twisted_edwards
-        self._bases: Optional[int] = None
-        self._bases_n = 0
+        self._bases_key = None  # (uid, version) of the DeviceBuffer whose points are resident
         self._seed = 0xB200
 
     # -- input helpers (src/curve-random.ts:24-91,151-194; src/parallel.ts:97-133,209-249)
@@ -54,8 +67,18 @@ class Parallel:
         self.engine.h2d(ptr, data)
         return DeviceBuffer(ptr, n)
 
+    def regeneratePointsFast(self, buf: DeviceBuffer, seed: Optional[int] = None) -> DeviceBuffer:
+        """randomPointsFast into an existing buffer (the reference regenerates at the same wasm offset after a
+        scope reset, scripts/msm-weierstrass.ts:12-22)."""
+        self.engine.random_points_device(buf.ptr, buf.n, self._next_seed(seed))
+        buf.touch()
+        return buf
+
     def free(self, buf: DeviceBuffer):
+        if self._bases_key is not None and self._bases_key[0] == buf.uid:
+            self._bases_key = None
         self.engine.dev_free(buf.ptr)
+        buf.ptr, buf.n = 0, 0
 
     def _next_seed(self, seed):
         if seed is not None:
@@ -68,9 +91,11 @@ class Parallel:
         options = options or {}
         if N > points.n or N > scalars.n:
             raise L.MsmError(L.E_INVALID, "N exceeds the input buffers")
-        if self._bases != points.ptr or self._bases_n < N:
+        if not points.ptr:
+            raise L.MsmError(L.E_INVALID, "points buffer was freed")
+        if self._bases_key != (points.uid, points.version):
             self.engine.set_bases_device(points.ptr, points.n, points.layout)
-            self._bases, self._bases_n = points.ptr, points.n
+            self._bases_key = (points.uid, points.version)
         res = self.engine.run(scalars.ptr, N, layout=scalars.layout, form=form,
                               window_bits=int(options.get("c", 0) or 0), on_device=True)
         log = [[f"{k[:-3]}... {v:.2f}ms"] for k, v in res.timing.items() if k.endswith("_ms")] if verbose else []

@@ -1,19 +1,26 @@
 /* N-API addon over the C ABI of libmsm_b200.so (include/msm_b200.h): the binding a maintainer of
- * mitschabaude/msm-zprize adds so that `Parallel.msm / msmUnsafe / msmProjective` run on the GPU
+ * mitschabaude/msm-zprize adds so that `Parallel.msm / msmUnsafe / msmProjective` run on the GPU(s)
  * (ts/msm-b200.ts is the TypeScript side; INTEGRATION.md explains the wiring).
  *
  * Only stable `napi_*` C functions are used.  Node is not part of this image, so this file is compile-
  * checked against napi/stub/node_api.h (tests/test_abi.py) and otherwise untested here; the tested binding
  * is the ctypes one (msm_zprize_b200/_lib.py) over the same entry points.
  *
- *   createContext(curveId, device)                                   -> External
- *   setBases(ctx, memoryBytes, byteOffset, n, layout)        (memoryBytes: the Uint8Array over the wasm memory)
+ *   createContext(curveId, devices)                                  -> External
+ *       devices: a device number or an array of them; the context is always a msm_b200_multi (one device is
+ *       the degenerate case), so one `run` fans out over all of them inside the library
+ *   setBases(ctx, memoryBytes, byteOffset, n, layout)                -> Promise<void>
  *   run(ctx, memoryBytes, byteOffset, n, layout, form, windowBits)   -> Promise<{x, y, isZero, timing}>
+ *       (memoryBytes: the Uint8Array over the wasm memory)
  *   destroy(ctx)
  *
- * `run` does its work in napi async work (off the event loop): the reference's msm is async as well
- * (src/msm-batched-affine.ts:74-83) and the main thread must stay responsive (src/threads/threads.ts:221-260).
- * Errors: a non-zero return code becomes a thrown Error / rejected Promise carrying msm_b200_last_error()
+ * `setBases` and `run` do their work in napi async work (off the event loop): the reference's msm is async as
+ * well (src/msm-batched-affine.ts:74-83) and the main thread must stay responsive
+ * (src/threads/threads.ts:221-260).  A context is single-caller like one thread pool of the reference: while
+ * a job is in flight a second setBases / run / destroy on the same context throws ("context busy") instead of
+ * racing on the workspace; every job holds a reference on the context External, so garbage collection cannot
+ * finalise a context under a running job.
+ * Errors: a non-zero return code becomes a thrown Error / rejected Promise carrying the library's message
  * (the reference throws from `assert`, src/util.ts:256, or traps).
  */
 #include <node_api.h>
@@ -31,47 +38,75 @@
     }                                                     \
   } while (0)
 
-static void finalize_ctx(napi_env env, void* data, void* hint) {
-  (void)env;
-  (void)hint;
-  if (data) msm_b200_destroy((msm_b200_ctx*)data);
-}
+#define MAX_DEVICES 64
 
-/* a slot that can be emptied by destroy() while the External is still referenced from JS */
+/* a slot that can be emptied by destroy() while the External is still referenced from JS; `busy` is only
+ * touched on the JS main thread (set when a job is queued, cleared in its completion callback) */
 typedef struct {
-  msm_b200_ctx* ctx;
+  msm_b200_multi* m;
+  int busy;
 } ctx_box;
 
 static void finalize_box(napi_env env, void* data, void* hint) {
+  (void)env;
+  (void)hint;
   ctx_box* box = (ctx_box*)data;
   if (box) {
-    finalize_ctx(env, box->ctx, hint);
+    if (box->m) msm_b200_multi_destroy(box->m);
     free(box);
   }
 }
 
-static msm_b200_ctx* unbox(napi_env env, napi_value v) {
+/* the context, or NULL with an exception pending; `for_job`: the caller is about to start work on it */
+static ctx_box* unbox(napi_env env, napi_value v, int for_job) {
   ctx_box* box = NULL;
-  if (napi_get_value_external(env, v, (void**)&box) != napi_ok || !box || !box->ctx) {
+  if (napi_get_value_external(env, v, (void**)&box) != napi_ok || !box || !box->m) {
     napi_throw_error(env, "MSM_B200", "invalid or destroyed context");
     return NULL;
   }
-  return box->ctx;
+  if (for_job && box->busy) {
+    napi_throw_error(env, "MSM_B200", "context busy: await the previous setBases() / run() first");
+    return NULL;
+  }
+  return box;
 }
 
 static napi_value CreateContext(napi_env env, napi_callback_info info) {
   size_t argc = 2;
   napi_value argv[2];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-  int32_t curve = 0, device = 0;
+  int32_t curve = 0;
+  int devices[MAX_DEVICES] = {0};
+  uint32_t n_dev = 1;
   NAPI_OK(napi_get_value_int32(env, argv[0], &curve));
-  if (argc > 1) NAPI_OK(napi_get_value_int32(env, argv[1], &device));
+  if (argc > 1) {
+    bool is_array = false;
+    NAPI_OK(napi_is_array(env, argv[1], &is_array));
+    if (is_array) {
+      NAPI_OK(napi_get_array_length(env, argv[1], &n_dev));
+      if (n_dev < 1 || n_dev > MAX_DEVICES) {
+        napi_throw_range_error(env, "MSM_B200", "devices: 1..64 entries");
+        return NULL;
+      }
+      for (uint32_t i = 0; i < n_dev; i++) {
+        napi_value e;
+        int32_t d = 0;
+        NAPI_OK(napi_get_element(env, argv[1], i, &e));
+        NAPI_OK(napi_get_value_int32(env, e, &d));
+        devices[i] = d;
+      }
+    } else {
+      int32_t d = 0;
+      NAPI_OK(napi_get_value_int32(env, argv[1], &d));
+      devices[0] = d;
+    }
+  }
   ctx_box* box = (ctx_box*)calloc(1, sizeof *box);
   if (!box) {
     napi_throw_error(env, "MSM_B200", "out of memory");
     return NULL;
   }
-  if (msm_b200_create(&box->ctx, curve, device, NULL) != MSM_OK) {
+  if (msm_b200_multi_create(&box->m, curve, devices, (int)n_dev) != MSM_OK) {
     free(box);
     napi_throw_error(env, "MSM_B200", msm_b200_global_error());
     return NULL;
@@ -87,9 +122,13 @@ static napi_value Destroy(napi_env env, napi_callback_info info) {
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   ctx_box* box = NULL;
   NAPI_OK(napi_get_value_external(env, argv[0], (void**)&box));
-  if (box && box->ctx) {
-    msm_b200_destroy(box->ctx);
-    box->ctx = NULL;
+  if (box && box->m) {
+    if (box->busy) {
+      napi_throw_error(env, "MSM_B200", "context busy: await the running call before destroy()");
+      return NULL;
+    }
+    msm_b200_multi_destroy(box->m);
+    box->m = NULL;
   }
   return NULL;
 }
@@ -113,47 +152,33 @@ static int region(napi_env env, napi_value view, napi_value off_v, size_t need, 
   return 0;
 }
 
-static napi_value SetBases(napi_env env, napi_callback_info info) {
-  size_t argc = 5;
-  napi_value argv[5];
-  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-  msm_b200_ctx* ctx = unbox(env, argv[0]);
-  if (!ctx) return NULL;
-  int64_t n = 0;
-  int32_t layout = 0;
-  NAPI_OK(napi_get_value_int64(env, argv[3], &n));
-  NAPI_OK(napi_get_value_int32(env, argv[4], &layout));
-  if (n < 0) {
-    napi_throw_range_error(env, "MSM_B200", "negative count");
-    return NULL;
-  }
-  uint8_t* p = NULL;
-  if (region(env, argv[1], argv[2], (size_t)n * msm_b200_point_bytes(ctx, layout), &p)) return NULL;
-  /* synchronous: one H2D copy + the ingest kernel; the caller reuses the bases over many run() calls */
-  if (msm_b200_set_bases(ctx, p, (size_t)n, layout, 0) != MSM_OK) napi_throw_error(env, "MSM_B200", msm_b200_last_error(ctx));
-  return NULL;
-}
-
+/* one asynchronous call on a context: setBases (is_run = 0) or run */
 typedef struct {
   napi_async_work work;
   napi_deferred deferred;
-  napi_ref keepalive; /* the memory view must outlive the copy */
-  msm_b200_ctx* ctx;
-  const uint8_t* scalars;
+  napi_ref keep_memory;  /* the memory view must outlive the copy */
+  napi_ref keep_context; /* the External must outlive the job (no finalisation under a running MSM) */
+  ctx_box* box;
+  int is_run;
+  const uint8_t* data;
   size_t n;
   int layout, form, window_bits;
   int rc;
   msm_b200_point out;
   msm_b200_timing tm;
   char err[256];
-} run_job;
+} job_t;
 
-static void run_execute(napi_env env, void* data) {
+static void job_execute(napi_env env, void* data) {
   (void)env;
-  run_job* j = (run_job*)data;
-  j->rc = msm_b200_run(j->ctx, j->scalars, j->n, j->layout, 0, j->form, j->window_bits, &j->out, &j->tm);
+  job_t* j = (job_t*)data;
+  msm_b200_multi* m = j->box->m;
+  if (j->is_run)
+    j->rc = msm_b200_multi_run(m, j->data, j->n, j->layout, j->form, j->window_bits, &j->out, &j->tm);
+  else
+    j->rc = msm_b200_multi_set_bases(m, j->data, j->n, j->layout);
   if (j->rc != MSM_OK) {
-    strncpy(j->err, msm_b200_last_error(j->ctx), sizeof j->err - 1);
+    strncpy(j->err, msm_b200_multi_last_error(m), sizeof j->err - 1);
     j->err[sizeof j->err - 1] = 0;
   }
 }
@@ -172,8 +197,9 @@ static void set_number(napi_env env, napi_value obj, const char* key, double v) 
   if (napi_create_double(env, v, &n) == napi_ok) napi_set_named_property(env, obj, key, n);
 }
 
-static void run_complete(napi_env env, napi_status status, void* data) {
-  run_job* j = (run_job*)data;
+static void job_complete(napi_env env, napi_status status, void* data) {
+  job_t* j = (job_t*)data;
+  j->box->busy = 0;
   if (status != napi_ok && j->rc == MSM_OK) {
     j->rc = MSM_E_STATE;
     strcpy(j->err, "async work cancelled");
@@ -183,8 +209,12 @@ static void run_complete(napi_env env, napi_status status, void* data) {
     napi_create_string_utf8(env, j->err, NAPI_AUTO_LENGTH, &msg);
     napi_create_error(env, NULL, msg, &err);
     napi_reject_deferred(env, j->deferred, err);
+  } else if (!j->is_run) {
+    napi_value undef;
+    napi_get_undefined(env, &undef);
+    napi_resolve_deferred(env, j->deferred, undef);
   } else {
-    const size_t fb = msm_b200_point_bytes(j->ctx, MSM_LAYOUT_LE_BYTES) / 2; /* 48 or 32 */
+    const size_t fb = msm_b200_point_bytes(msm_b200_multi_ctx(j->box->m, 0), MSM_LAYOUT_LE_BYTES) / 2; /* 48 or 32 */
     napi_value res, tm, zero;
     napi_create_object(env, &res);
     napi_set_named_property(env, res, "x", bytes_value(env, j->out.x, fb));
@@ -203,55 +233,89 @@ static void run_complete(napi_env env, napi_status status, void* data) {
     set_number(env, tm, "windowBits", j->tm.window_bits);
     set_number(env, tm, "windows", j->tm.n_windows);
     set_number(env, tm, "rounds", j->tm.rounds);
+    set_number(env, tm, "devices", msm_b200_multi_devices(j->box->m));
     napi_set_named_property(env, res, "timing", tm);
     napi_resolve_deferred(env, j->deferred, res);
   }
-  napi_delete_reference(env, j->keepalive);
+  napi_delete_reference(env, j->keep_memory);
+  napi_delete_reference(env, j->keep_context);
   napi_delete_async_work(env, j->work);
   free(j);
 }
 
-static napi_value Run(napi_env env, napi_callback_info info) {
+/* shared by setBases and run: argv = ctx, memoryBytes, byteOffset, n, layout [, form, windowBits] */
+static napi_value start_job(napi_env env, napi_callback_info info, int is_run) {
   size_t argc = 7;
   napi_value argv[7];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-  msm_b200_ctx* ctx = unbox(env, argv[0]);
-  if (!ctx) return NULL;
+  if (argc < 5) {
+    napi_throw_type_error(env, "MSM_B200", "expected (ctx, memoryBytes, byteOffset, n, layout, ...)");
+    return NULL;
+  }
+  ctx_box* box = unbox(env, argv[0], 1);
+  if (!box) return NULL;
   int64_t n = 0;
   int32_t layout = 0, form = 0, c = 0;
   NAPI_OK(napi_get_value_int64(env, argv[3], &n));
   NAPI_OK(napi_get_value_int32(env, argv[4], &layout));
-  NAPI_OK(napi_get_value_int32(env, argv[5], &form));
-  if (argc > 6) NAPI_OK(napi_get_value_int32(env, argv[6], &c));
+  if (is_run && argc > 5) NAPI_OK(napi_get_value_int32(env, argv[5], &form));
+  if (is_run && argc > 6) NAPI_OK(napi_get_value_int32(env, argv[6], &c));
   if (n < 0) {
     napi_throw_range_error(env, "MSM_B200", "negative count");
     return NULL;
   }
+  msm_b200_ctx* c0 = msm_b200_multi_ctx(box->m, 0);
+  const size_t item = is_run ? msm_b200_scalar_bytes(c0, layout) : msm_b200_point_bytes(c0, layout);
   uint8_t* p = NULL;
-  if (region(env, argv[1], argv[2], (size_t)n * msm_b200_scalar_bytes(ctx, layout), &p)) return NULL;
-  run_job* j = (run_job*)calloc(1, sizeof *j);
+  if (region(env, argv[1], argv[2], (size_t)n * item, &p)) return NULL;
+  job_t* j = (job_t*)calloc(1, sizeof *j);
   if (!j) {
     napi_throw_error(env, "MSM_B200", "out of memory");
     return NULL;
   }
-  j->ctx = ctx;
-  j->scalars = p;
+  j->box = box;
+  j->is_run = is_run;
+  j->data = p;
   j->n = (size_t)n;
   j->layout = layout;
   j->form = form;
   j->window_bits = c;
   napi_value promise, name;
   if (napi_create_promise(env, &j->deferred, &promise) != napi_ok ||
-      napi_create_reference(env, argv[1], 1, &j->keepalive) != napi_ok ||
-      napi_create_string_utf8(env, "msm_b200_run", NAPI_AUTO_LENGTH, &name) != napi_ok ||
-      napi_create_async_work(env, NULL, name, run_execute, run_complete, j, &j->work) != napi_ok ||
-      napi_queue_async_work(env, j->work) != napi_ok) {
+      napi_create_reference(env, argv[1], 1, &j->keep_memory) != napi_ok) {
     free(j);
-    napi_throw_error(env, "MSM_B200", "could not queue the MSM");
+    napi_throw_error(env, "MSM_B200", "could not queue the call");
+    return NULL;
+  }
+  if (napi_create_reference(env, argv[0], 1, &j->keep_context) != napi_ok) {
+    napi_delete_reference(env, j->keep_memory);
+    free(j);
+    napi_throw_error(env, "MSM_B200", "could not queue the call");
+    return NULL;
+  }
+  if (napi_create_string_utf8(env, is_run ? "msm_b200_run" : "msm_b200_set_bases", NAPI_AUTO_LENGTH, &name) != napi_ok ||
+      napi_create_async_work(env, NULL, name, job_execute, job_complete, j, &j->work) != napi_ok) {
+    napi_delete_reference(env, j->keep_memory);
+    napi_delete_reference(env, j->keep_context);
+    free(j);
+    napi_throw_error(env, "MSM_B200", "could not queue the call");
+    return NULL;
+  }
+  box->busy = 1;
+  if (napi_queue_async_work(env, j->work) != napi_ok) {
+    box->busy = 0;
+    napi_delete_async_work(env, j->work);
+    napi_delete_reference(env, j->keep_memory);
+    napi_delete_reference(env, j->keep_context);
+    free(j);
+    napi_throw_error(env, "MSM_B200", "could not queue the call");
     return NULL;
   }
   return promise;
 }
+
+static napi_value SetBases(napi_env env, napi_callback_info info) { return start_job(env, info, 0); }
+static napi_value Run(napi_env env, napi_callback_info info) { return start_job(env, info, 1); }
 
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor props[] = {

@@ -52,6 +52,10 @@ napi_status napi_create_external(napi_env env, void* data, napi_finalize finaliz
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value* result);
+napi_status napi_is_array(napi_env env, napi_value value, bool* result);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value* result);
+napi_status napi_get_undefined(napi_env env, napi_value* result);
 napi_status napi_create_object(napi_env env, napi_value* result);
 napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
 napi_status napi_create_double(napi_env env, double value, napi_value* result);

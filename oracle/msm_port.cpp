@@ -923,6 +923,172 @@ struct Te {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Seeded synthetic inputs on the CPU: the same counter-based construction as the CUDA generators
+// (msm_zprize_b200/csrc/kernels_basic.cuh k_rp_tables / k_rp_points / k_random_scalars, which replace
+// randomPointsFast / randomScalars, src/curve-random.ts:24-91,151-194), so that the reference arm of
+// bench.py gets byte-identical inputs without loading the CUDA library.
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static const int RP_TABLES = 4, RP_BITS = 13;
+
+template <int N>
+static void gen_scalars(const Curve<N>& c, uint8_t* out, size_t first, size_t n, uint64_t seed, int T) {
+  const int qbits = c.pp.scalar_bits;
+  parallel_for(T, [&](int t) {
+    size_t lo, hi;
+    range_of(n, t, T, lo, hi);
+    for (size_t i = lo; i < hi; i++) {
+      uint64_t st = seed + (uint64_t)(first + i + 1) * 0xD1342543DE82EF95ull;
+      Big s;
+      for (;;) {
+        s = Big();
+        for (int j = 0; j < 4; j++) s.v[j] = splitmix64(st);
+        const int top = qbits - 224;  // bits kept in the top 32-bit word
+        uint64_t m = top >= 32 ? 0xFFFFFFFFull : ((1ull << top) - 1);
+        s.v[3] = (s.v[3] & 0xFFFFFFFFull) | ((s.v[3] >> 32) & m) << 32;
+        if (big_cmp(s, c.q) < 0) break;
+      }
+      s.to_le(out + 32 * i, 32);
+    }
+  });
+}
+
+// point arithmetic the generator needs, for both curve forms: accumulators are projective (Weierstrass,
+// 3N+1 words) or extended (twisted Edwards, 4N words); table entries are affine x | y (2N words, Montgomery)
+template <int N>
+struct GenOps {
+  typedef Curve<N> C;
+  static int acc_words(const C& c) { return c.pp.is_te ? 4 * N : 3 * N + 1; }
+  static void zero(const C& c, uint32_t* A) {
+    if (c.pp.is_te) Te<N>::zero(c, A);
+    else Weier<N>::p_zero(A);
+  }
+  static void add_xy(const C& c, uint32_t* A, const uint32_t* xy) {
+    if (c.pp.is_te) {
+      uint32_t Q[4 * N];
+      memcpy(Q, xy, 2 * N * 4);
+      memcpy(Q + 2 * N, c.F.one, N * 4);
+      c.F.mul(Q + 3 * N, xy, xy + N);
+      Te<N>::add(c, A, A, Q, true, false);
+    } else {
+      uint32_t Q[2 * N + 1];
+      memcpy(Q, xy, 2 * N * 4);
+      Q[2 * N] = 1;
+      Weier<N>::p_add_affine(c, A, A, Q, false);
+    }
+  }
+  static void dbl(const C& c, uint32_t* A) {
+    if (c.pp.is_te) Te<N>::add(c, A, A, A, false, false);
+    else Weier<N>::p_double(c, A, A);
+  }
+  static bool is_inf(const C& c, const uint32_t* A) { return !c.pp.is_te && (A[3 * N] == 0 || c.F.is_zero(A + 2 * N)); }
+  // affine x | y (Montgomery, reduced) of m accumulators with one shared inversion
+  static void normalise(const C& c, const uint32_t* A, size_t m, uint32_t* xy) {
+    const Field<N>& F = c.F;
+    const int AW = acc_words(c);
+    std::vector<uint32_t> pre(m * N);
+    uint32_t run[N], inv[N], zi[N];
+    memcpy(run, F.one, sizeof run);
+    for (size_t u = 0; u < m; u++) {
+      memcpy(pre.data() + u * N, run, N * 4);
+      F.mul(run, run, A + u * AW + 2 * N);
+    }
+    F.inverse(inv, run);
+    for (size_t u = m; u-- > 0;) {
+      F.mul(zi, inv, pre.data() + u * N);
+      F.mul(inv, inv, A + u * AW + 2 * N);
+      F.mul(xy + u * 2 * N, A + u * AW, zi);
+      F.mul(xy + u * 2 * N + N, A + u * AW + N, zi);
+      F.reduce(xy + u * 2 * N);
+      F.reduce(xy + u * 2 * N + N);
+    }
+  }
+};
+
+template <int N>
+static void gen_points(const Curve<N>& c, const uint8_t* gx_le, const uint8_t* gy_le, uint8_t* out, size_t first, size_t n,
+                       uint64_t seed, int nb, int T) {
+  typedef GenOps<N> G;
+  const Field<N>& F = c.F;
+  const int AW = G::acc_words(c);
+  uint32_t gxy[2 * N];
+  F.to_mont(gxy, Big::from_le(gx_le, 64));
+  F.to_mont(gxy + N, Big::from_le(gy_le, 64));
+  F.reduce(gxy);
+  F.reduce(gxy + N);
+  // tables: entry (k, j) = (j + 1) * B_k, B_k = h_k * G
+  const size_t E = (size_t)1 << RP_BITS;
+  std::vector<uint32_t> tables((size_t)RP_TABLES * E * 2 * N);
+  parallel_for(std::min(T, RP_TABLES), [&](int t) {
+    size_t klo, khi;
+    range_of(RP_TABLES, t, std::min(T, RP_TABLES), klo, khi);
+    for (size_t k = klo; k < khi; k++) {
+      uint64_t st = seed ^ (0xA5A5A5A5ull + k);
+      uint64_t h = splitmix64(st) | 1ull;
+      std::vector<uint32_t> acc(AW), bk(2 * N);
+      G::zero(c, acc.data());
+      bool started = false;
+      for (int bit = 63; bit >= 0; bit--) {
+        if (started) G::dbl(c, acc.data());
+        if ((h >> bit) & 1) {
+          G::add_xy(c, acc.data(), gxy);
+          started = true;
+        }
+      }
+      G::normalise(c, acc.data(), 1, bk.data());
+      // multiples of B_k, normalised in batches
+      const size_t BATCH = 256;
+      std::vector<uint32_t> accs(BATCH * AW);
+      std::vector<uint32_t> cur(AW);
+      G::zero(c, cur.data());
+      for (size_t j0 = 0; j0 < E; j0 += BATCH) {
+        for (size_t u = 0; u < BATCH; u++) {
+          G::add_xy(c, cur.data(), bk.data());
+          memcpy(accs.data() + u * AW, cur.data(), AW * 4);
+        }
+        G::normalise(c, accs.data(), BATCH, tables.data() + (k * E + j0) * 2 * N);
+      }
+    }
+  });
+  const uint64_t pseed = seed ^ 0x5EEDull;
+  parallel_for(T, [&](int t) {
+    size_t lo, hi;
+    range_of(n, t, T, lo, hi);
+    const size_t BATCH = 256;
+    std::vector<uint32_t> accs(BATCH * AW), xy(BATCH * 2 * N);
+    for (size_t i0 = lo; i0 < hi; i0 += BATCH) {
+      size_t m = std::min(BATCH, hi - i0);
+      for (size_t u = 0; u < m; u++) {
+        uint64_t st = pseed + (uint64_t)(first + i0 + u + 1) * 0xD1342543DE82EF95ull;
+        uint64_t r = splitmix64(st);
+        uint32_t* acc = accs.data() + u * AW;
+        G::zero(c, acc);
+        for (int k = 0; k < RP_TABLES; k++) {
+          uint32_t w = (uint32_t)(r >> (RP_BITS * k)) & ((1u << RP_BITS) - 1u);
+          G::add_xy(c, acc, tables.data() + ((size_t)k * E + w) * 2 * N);
+        }
+        if (G::is_inf(c, acc)) {
+          G::zero(c, acc);
+          G::add_xy(c, acc, gxy);
+        }
+      }
+      G::normalise(c, accs.data(), m, xy.data());
+      for (size_t u = 0; u < m; u++) {
+        F.from_mont(xy.data() + u * 2 * N).to_le(out + (i0 + u) * 2 * nb, nb);
+        F.from_mont(xy.data() + u * 2 * N + N).to_le(out + (i0 + u) * 2 * nb + nb, nb);
+      }
+    }
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // C API (loaded with ctypes by oracle/port.py)
 // ---------------------------------------------------------------------------------------------
@@ -1030,6 +1196,23 @@ int port_msm(void* h, const uint8_t* scalars_le, const uint32_t* points, size_t 
     z = run_msm(ctx->c9, scalars_le, points, n, threads, window_bits, form, out_x, out_y, nbytes);
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return z;
+}
+// seeded inputs, byte-identical to msm_b200_random_scalars / msm_b200_random_points (LE_BYTES layout)
+// (`first`: global index of the first element, so that a range of a larger set can be generated)
+void port_random_scalars(void* h, uint8_t* out_le, size_t first, size_t n, uint64_t seed, int threads) {
+  PortCtx* ctx = (PortCtx*)h;
+  if (ctx->n29 == 14)
+    gen_scalars(ctx->c14, out_le, first, n, seed, threads);
+  else
+    gen_scalars(ctx->c9, out_le, first, n, seed, threads);
+}
+void port_random_points(void* h, const uint8_t* gx_le64, const uint8_t* gy_le64, uint8_t* out_le, size_t first, size_t n,
+                        uint64_t seed, int nbytes, int threads) {
+  PortCtx* ctx = (PortCtx*)h;
+  if (ctx->n29 == 14)
+    gen_points(ctx->c14, gx_le64, gy_le64, out_le, first, n, seed, nbytes, threads);
+  else
+    gen_points(ctx->c9, gx_le64, gy_le64, out_le, first, n, seed, nbytes, threads);
 }
 // single field multiplication throughput (ns per Montgomery product), for the record
 double port_mul_ns(void* h, int iters) {

@@ -30,6 +30,9 @@ def _lib():
     L.port_points_from_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
     L.port_msm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
                            C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.port_random_scalars.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint64, C.c_int]
+    L.port_random_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint64,
+                                     C.c_int, C.c_int]
     L.port_mul_ns.restype = C.c_double
     L.port_mul_ns.argtypes = [C.c_void_p, C.c_int]
     return L
@@ -67,6 +70,7 @@ class Port:
             self.nbytes, n29 = (32 if curve == "pallas" else 48), O.montgomery_params(P.p).n
             self.field_bits = O.log2(P.p)
         self.q = P.q
+        self.gx, self.gy = P.gx, P.gy
         self.h = self.L.port_create(C.byref(pp), n29)
         self.point_words = self.L.port_point_words(self.h)
 
@@ -105,6 +109,19 @@ class Port:
         z = self.L.port_msm(self.h, src, points, n, threads, c, form, ox, oy, self.nbytes, C.byref(sec))
         return (int.from_bytes(bytes(ox)[: self.nbytes], "little"), int.from_bytes(bytes(oy)[: self.nbytes], "little"),
                 bool(z), sec.value)
+
+    # -- seeded inputs, byte-identical to the CUDA generators (msm_b200_random_points / _scalars)
+    def random_scalars(self, n: int, seed: int, threads: int = 1, first: int = 0) -> bytes:
+        out = (C.c_uint8 * (32 * max(n, 1)))()
+        self.L.port_random_scalars(self.h, out, first, n, seed & (2**64 - 1), threads)
+        return bytes(out)[: 32 * n]
+
+    def random_points(self, n: int, seed: int, threads: int = 1, first: int = 0) -> bytes:
+        out = (C.c_uint8 * (2 * self.nbytes * max(n, 1)))()
+        gx = (C.c_uint8 * 64).from_buffer_copy(self.gx.to_bytes(64, "little"))
+        gy = (C.c_uint8 * 64).from_buffer_copy(self.gy.to_bytes(64, "little"))
+        self.L.port_random_points(self.h, gx, gy, out, first, n, seed & (2**64 - 1), self.nbytes, threads)
+        return bytes(out)[: 2 * self.nbytes * n]
 
     def mul_ns(self, iters: int = 200000) -> float:
         return self.L.port_mul_ns(self.h, iters)

@@ -18,8 +18,8 @@ def lib():
     return _lib.lib()
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "msm_b200.h")).read()
+def _declared(header="msm_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(msm_b200_[a-z0-9_]+)\s*\(", src)))
 
@@ -27,10 +27,15 @@ def _declared():
 def test_every_declared_symbol_is_exported(lib):
     from msm_zprize_b200 import _lib
     names = _declared()
-    assert len(names) >= 20
+    assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.EXPORTS) == names
+    # the test / measurement hooks live in their own header, outside the drop-in boundary
+    hooks = _declared("msm_b200_test.h")
+    assert sorted(_lib.TEST_EXPORTS) == hooks and not set(hooks) & set(names)
+    for n in hooks:
+        assert hasattr(lib, n), n
 
 
 def test_struct_sizes_match_header(lib):

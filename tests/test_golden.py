@@ -87,3 +87,27 @@ def test_parallel_mirror_reads_like_the_reference():
     r = T.Parallel.msm(sc, pts, 256)["result"]
     assert not r.is_zero
     T.close()
+
+
+@pytest.mark.gpu
+def test_parallel_bases_cache_follows_contents_not_addresses():
+    """free -> allocate again (cudaMalloc hands the same address out) -> other points: the mirror must not
+    answer with the MSM of the old points; the same for points regenerated in place."""
+    import msm_zprize_b200.parallel as P
+    B = P.create_weierstrass("pallas")
+    N = 512
+    sc = B.Parallel.randomScalars(N, seed=5)
+    p1 = B.Parallel.randomPointsFast(N, seed=1)
+    a = B.Parallel.msm(sc, p1, N)["result"]
+    B.Parallel.free(p1)
+    p2 = B.Parallel.randomPointsFast(N, seed=2)  # very likely the same device address
+    b = B.Parallel.msm(sc, p2, N)["result"]
+    fresh = P.create_weierstrass("pallas")
+    sc2 = fresh.Parallel.randomScalars(N, seed=5)
+    want = fresh.Parallel.msm(sc2, fresh.Parallel.randomPointsFast(N, seed=2), N)["result"]
+    assert (b.x, b.y) == (want.x, want.y) and (a.x, a.y) != (b.x, b.y)
+    B.Parallel.regeneratePointsFast(p2, seed=1)
+    c = B.Parallel.msm(sc, p2, N)["result"]
+    assert (c.x, c.y) == (a.x, a.y)
+    B.close()
+    fresh.close()

@@ -60,6 +60,24 @@ def test_generated_te_inputs(mz):
         assert (res.x, res.y) == te.to_affine(O.msm(te, S, [te.from_affine(p) for p in P]))
 
 
+@pytest.mark.parametrize("name", ["bls12-377", "pallas", "bls12-381", "ed-on-bls12-377"])
+def test_device_generators_equal_the_cpu_port_generators(mz, name):
+    """`bench.py --impl reference` never loads the CUDA library: it draws its inputs from the CPU port's
+    generators.  They must be byte-identical to the device generators, also for a range of a larger set."""
+    from oracle.port import Port
+    port = Port(name)
+    n = 3000
+    with mz.MsmEngine(name) as eng:
+        d_pts, d_sc, pts, sc = _gen(eng, mz, n, 0xB212)
+        assert pts == port.random_points(n, 0xB212, 4)
+        assert sc == port.random_scalars(n, 0xB213, 4)
+        pb = eng.point_bytes(mz.LAYOUT_LE_BYTES)
+        eng.random_points_device(d_pts, 500, 0xB212, first=2500)
+        eng.random_scalars_device(d_sc, 500, 0xB213, first=2500)
+        assert eng.d2h(d_pts, 500 * pb).tobytes() == pts[2500 * pb:]
+        assert eng.d2h(d_sc, 500 * 32).tobytes() == sc[2500 * 32:]
+
+
 @pytest.mark.parametrize("name,lg", [("bls12-377", 16), ("pallas", 16), ("ed-on-bls12-377", 16), ("bls12-381", 15)])
 def test_large_n_properties(mz, name, lg):
     """n = 2^16: (i) the result does not depend on the window size, (ii) linearity:
@@ -136,6 +154,36 @@ def test_full_size_against_cpu_port(mz, name, lg):
     prep = port.prepare_points(pts, n, threads)
     x, y, z, _ = port.msm(sc, prep, n, threads)
     assert (got.x, got.y, got.is_zero) == (x, y, z)
+
+
+@pytest.mark.parametrize("name,lg", [("pallas", 20), ("bls12-377", 20), ("ed-on-bls12-377", 20)])
+def test_reference_ceiling_sizes_against_cpu_port(mz, name, lg):
+    """The largest sizes the reference itself runs (doc/zprize23.md:27: 2^20; BASELINE.json configs 3-5): the GPU
+    result must equal the C++ port of the reference algorithm on the same seeded inputs, with the reference's
+    window table on the CPU side (BLS12-377 c=18, Pallas c=19, ed-on-bls12-377 c=19).  Inputs come from the two
+    generators independently (device for the GPU, port for the CPU)."""
+    import os
+    from oracle.port import Port
+    n = 1 << lg
+    threads = os.cpu_count() or 1
+    port = Port(name)
+    pts = port.random_points(n, 0xB200 + lg, threads)
+    sc = port.random_scalars(n, 0x5CA1A + lg, threads)
+    x, y, z, _ = port.msm(sc, port.prepare_points(pts, n, threads), n, threads)
+    with mz.MsmEngine(name) as eng:
+        pb = eng.point_bytes(mz.LAYOUT_LE_BYTES)
+        d_pts = eng.dev_alloc(n * pb)
+        d_sc = eng.dev_alloc(n * 32)
+        eng.random_points_device(d_pts, n, 0xB200 + lg)
+        eng.random_scalars_device(d_sc, n, 0x5CA1A + lg)
+        eng.set_bases_device(d_pts, n)
+        got = eng.run(d_sc, n, on_device=True)
+        assert (got.x, got.y, got.is_zero) == (x, y, z)
+        # and through the host-buffer entry point with the port's bytes (what a caller of compute_msm passes)
+        got2 = eng.msm(sc, pts, n)
+        assert (got2.x, got2.y, got2.is_zero) == (x, y, z)
+        eng.dev_free(d_sc)
+        eng.dev_free(d_pts)
 
 
 @pytest.mark.parametrize("name", ["bls12-377", "pallas", "bls12-381", "ed-on-bls12-377"])

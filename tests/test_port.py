@@ -57,3 +57,45 @@ def test_port_window_policy_matches_reference_table():
     assert Port("bls12-377").default_window(1 << 20) == 18
     assert Port("pallas").default_window(1 << 16) == 12
     assert Port("ed-on-bls12-377").default_window(1 << 16) == 14
+
+
+M64 = 2 ** 64 - 1
+
+
+def _splitmix(st):
+    st = (st + 0x9E3779B97F4A7C15) & M64
+    z = st
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return st, z ^ (z >> 31)
+
+
+@pytest.mark.parametrize("name", ["bls12-377", "pallas", "bls12-381", "ed-on-bls12-377"])
+def test_port_seeded_generators(name):
+    """The port's input generators (what `bench.py --impl reference` feeds the CPU arm with) restate the CUDA
+    generators' construction: point i = sum_k (w_k + 1) * h_k * G with 13-bit w_k from SplitMix64 -- checked here
+    against scalar multiplication in the python oracle; scalars uniform below q; ranges of a larger set agree."""
+    port = Port(name)
+    seed, n, nb = 0xB212, 300, port.nbytes
+    pts = port.random_points(n, seed, 4)
+    hs = []
+    for k in range(4):
+        _, h = _splitmix(seed ^ (0xA5A5A5A5 + k))
+        hs.append(h | 1)
+    for i in (0, 1, 255, 256, 299):  # both sides of the generator's batch boundary
+        _, r = _splitmix(((seed ^ 0x5EED) + (i + 1) * 0xD1342543DE82EF95) & M64)
+        s = sum(hs[k] * (((r >> (13 * k)) & 8191) + 1) for k in range(4))
+        got = (int.from_bytes(pts[2 * nb * i:2 * nb * i + nb], "little"),
+               int.from_bytes(pts[2 * nb * i + nb:2 * nb * (i + 1)], "little"))
+        if name == "ed-on-bls12-377":
+            te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+            want = te.to_affine(te.scale(s % te.q, te.one))
+        else:
+            aff = O.WeierstrassAffine({"bls12-377": O.BLS12_377, "pallas": O.PALLAS, "bls12-381": O.BLS12_381}[name])
+            want = aff.scale(s % aff.q, aff.one)
+        assert got == tuple(want)
+    sc = port.random_scalars(n, 77, 3)
+    vals = [int.from_bytes(sc[32 * i:32 * i + 32], "little") for i in range(n)]
+    assert max(vals) < port.q and len(set(vals)) == n
+    assert port.random_points(40, seed, 2, first=260) == pts[260 * 2 * nb:]
+    assert port.random_scalars(40, 77, 2, first=260) == sc[260 * 32:]

@@ -43,30 +43,47 @@ function toLog(timing: Timing, verbose: boolean): any[][] {
     .map(([k, v]) => [`${k}... ${v.toFixed(2)}ms`]);
 }
 
-/** Resident-bases bookkeeping shared by the three entry points: the benchmark drivers reuse `pointPtr`
- *  over many runs with fresh scalars (scripts/msm-weierstrass.ts:19,29-33). */
+/** Resident-bases bookkeeping shared by the three entry points.  The benchmark drivers reuse `pointPtr` over
+ *  many runs with fresh scalars (scripts/msm-weierstrass.ts:19,29-33), so the upload + ingest is worth
+ *  skipping -- but a wasm address says nothing about its contents (`using ... atCurrentOffset` resets hand the
+ *  same offset out again, and randomPointsFast can rewrite a region in place).  Residency is therefore keyed
+ *  on a caller-supplied generation: pass `options.basesGeneration` (any value that changes whenever the
+ *  points at `pointPtr` change) to keep the bases resident across calls; WITHOUT it every call uploads the
+ *  points again, which is what the reference's msm does (it reads the points on every call). */
 function makeRunner(ctx: unknown, Field: any, Scalar: any) {
-  let basesPtr = -1, basesN = 0;
-  return async function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number) {
-    if (pointPtr !== basesPtr || N > basesN) {
-      addon.setBases(ctx, Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
-      basesPtr = pointPtr;
-      basesN = N;
-    }
-    return (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
+  let basesKey: string | undefined;
+  let chain: Promise<unknown> = Promise.resolve(); // one call in flight per context (the addon rejects overlap)
+  return function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number, generation?: unknown) {
+    const job = chain.then(async () => {
+      const key = generation === undefined ? undefined : `${String(generation)}:${pointPtr}:${N}`;
+      if (key === undefined || key !== basesKey) {
+        basesKey = undefined;
+        await addon.setBases(ctx, Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
+        basesKey = key;
+      }
+      return (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
+    });
+    chain = job.catch(() => undefined);
+    return job;
   };
 }
 
+type MsmOptions = { c?: number; basesGeneration?: unknown };
+
 /** Weierstraß curves: drop-in for `createMsm(Inputs)` plus `msmProjective`. */
-export function createMsmB200(Inputs: any, curveId: number, device = 0) {
+export function createMsmB200(Inputs: any, curveId: number, devices: number | number[] = 0) {
   const { Field, Scalar, Affine, Projective } = Inputs;
-  const ctx = addon.createContext(curveId, device);
+  // several devices: ONE msm() call range-shards the points over them inside the library (one host thread per
+  // GPU, NCCL gather of the partial points, sum on the first device) -- the shape of the reference's SPMD call
+  // over its thread pool (src/threads/threads.ts:354-359, src/msm-batched-affine.ts:294-322)
+  const ctx = addon.createContext(curveId, devices);
   const run = makeRunner(ctx, Field, Scalar);
 
-  async function call(scalarPtr: number, pointPtr: number, N: number, verbose: boolean, form: number, c: number) {
+  async function call(scalarPtr: number, pointPtr: number, N: number, verbose: boolean, form: number,
+                      { c = 0, basesGeneration }: MsmOptions) {
     // allocated before the scope so it survives it, like the reference's `result` (src/msm-batched-affine.ts:87-90)
     const result = Field.global.getPointer(Projective.size);
-    const r = await run(scalarPtr, pointPtr, N, form, c);
+    const r = await run(scalarPtr, pointPtr, N, form, c, basesGeneration);
     using _ = Field.local.atCurrentOffset;
     const affine = Field.local.getPointer(Affine.size);
     // canonical (x, y) -> Montgomery affine point -> projective with Z = mg1 (src/curve-affine.ts:273-284,
@@ -76,24 +93,24 @@ export function createMsmB200(Inputs: any, curveId: number, device = 0) {
     return { result, log: toLog(r.timing, verbose) };
   }
 
-  const msm = (scalarPtr: number, pointPtr: number, N: number, verbose = false, { c = 0 }: { c?: number } = {}) =>
-    call(scalarPtr, pointPtr, N, verbose, FORM_AFFINE_GLV, c);
-  const msmProjective = (scalarPtr: number, pointPtr: number, N: number, { c = 0 }: { c?: number } = {}) =>
-    call(scalarPtr, pointPtr, N, false, FORM_PROJECTIVE, c);
+  const msm = (scalarPtr: number, pointPtr: number, N: number, verbose = false, options: MsmOptions = {}) =>
+    call(scalarPtr, pointPtr, N, verbose, FORM_AFFINE_GLV, options);
+  const msmProjective = (scalarPtr: number, pointPtr: number, N: number, options: MsmOptions = {}) =>
+    call(scalarPtr, pointPtr, N, false, FORM_PROJECTIVE, options);
   // the engine always applies the safe addition rules (batchAddNew, src/curve-affine.ts:376-458), which agree
   // with the unsafe ones wherever those are defined
   return { msm, msmUnsafe: msm, msmProjective, destroy: () => addon.destroy(ctx) };
 }
 
 /** Twisted Edwards (ed-on-bls12-377): drop-in for `createMsmBasic(Inputs)` (src/msm-basic.ts:34-43). */
-export function createMsmBasicB200(Inputs: any, device = 0) {
+export function createMsmBasicB200(Inputs: any, devices: number | number[] = 0) {
   const { Field, Scalar, Curve } = Inputs;
-  const ctx = addon.createContext(CURVE_ED_ON_BLS12_377, device);
+  const ctx = addon.createContext(CURVE_ED_ON_BLS12_377, devices);
   const run = makeRunner(ctx, Field, Scalar);
 
-  async function msm(scalarPtr: number, pointPtr: number, N: number, { c = 0 }: { c?: number } = {}) {
+  async function msm(scalarPtr: number, pointPtr: number, N: number, { c = 0, basesGeneration }: MsmOptions = {}) {
     const result = Field.global.getPointer(Curve.size);
-    const r = await run(scalarPtr, pointPtr, N, FORM_TE_EXTENDED, c);
+    const r = await run(scalarPtr, pointPtr, N, FORM_TE_EXTENDED, c, basesGeneration);
     const x = bytesToBigint(r.x), y = bytesToBigint(r.y);
     // extended coordinates of the affine result: (x, y, 1, x*y)  (src/curve-twisted-edwards.ts:435-447)
     Curve.fromBigint(result, { X: x, Y: y, Z: 1n, T: (x * y) % Field.p });
