@@ -79,6 +79,8 @@ typedef struct msm_b200_timing {
   int n_windows;            /* K */
   int rounds;               /* batched-affine tree rounds */
   unsigned long long n_adds;/* point additions finished inside the dominant kernel's launches */
+  int shared_buckets;       /* 1: resident window tables 2^(kc) G were used, all windows share one bucket set */
+  int reserved;
 } msm_b200_timing;
 
 /* Result point, canonical affine (the normalisation that defines parity: Projective.toAffine +
@@ -108,7 +110,12 @@ const char* msm_b200_global_error(void);
  * benchmark iterations, scripts/msm-weierstrass.ts:19,29-33).  Does on the device what
  * preparePointsAndScalars does per point (copy, endomorphism; src/msm-batched-affine.ts:338-409)
  * and, for LE_BYTES, what Parallel.pointsFromBytes does (src/parallel.ts:97-116,209-232).
- * `points` is host memory unless `on_device` != 0. */
+ * `points` is host memory unless `on_device` != 0.
+ * For GLV curves with 2^14 <= n <= 2^21 points this call also builds the window tables 2^(kc) G_i of the set
+ * (K - 1 more record sets in device memory, about three MSMs of work, once): later msm_b200_run calls with the
+ * default window then add the digits of all windows into one shared set of buckets (timing.shared_buckets = 1;
+ * same point, shorter bucket reduction, no Horner step).  MSM_B200_TABLES=0 in the environment turns this off;
+ * the one-shot msm_b200_msm never builds tables. */
 int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device);
 /* Same for host points, without waiting: the copy and the ingest kernel are queued on the context's copy
  * stream and the next run / run_partial waits for them only where it first reads a base point, i.e. behind its

@@ -51,7 +51,7 @@ static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int l
       rc = fail(ctx, MSM_E_CUDA, "H2D copy of the points failed");
     d_in = ctx->raw_points.p;
   }
-  if (rc == 0) rc = ops_of(ctx->curve)->ingest(ctx, d_in, n, layout);
+  if (rc == 0) rc = ops_of(ctx->curve)->ingest(ctx, d_in, n, layout, /*tables=*/!overlapped);
   if (overlapped) {
     if (rc == 0 && cudaEventRecord(ctx->bases_ready, ctx->copy_stream) == cudaSuccess) ctx->bases_pending = true;
     ctx->stream = main_stream;
@@ -94,6 +94,7 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
   ctx->pending.valid = false;
   ctx->pending.window_bits = c;
   ctx->pending.n_windows = 0;
+  ctx->pending.shared_buckets = 0;
   if (n == 0)
     rc = ops_of(ctx->curve)->zero_partial(ctx);
   else
@@ -181,6 +182,8 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = std::min(std::max(1, atoi(e)), (int)ACC_MAX_PAIRS);
   if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = std::min(std::max(1, atoi(e)), 5);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = std::min(std::max(1, atoi(e)), 5);
+  if (const char* e = getenv("MSM_B200_TABLES")) ctx->tables_enabled = atoi(e) != 0;
+  if (const char* e = getenv("MSM_B200_TABLE_MAX_LOG2N")) ctx->table_max_log2n = std::min(std::max(0, atoi(e)), 26);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)std::max(1ll, atoll(e));
   if (stream) {
     ctx->stream = (cudaStream_t)stream;

@@ -30,7 +30,7 @@ struct PendingTiming {
   bool valid = false;
   int e[5] = {0, 0, 0, 0, 0};  // digits | sort | accumulate | reduce boundaries
   std::vector<std::pair<int, int>> hot;
-  int window_bits = 0, n_windows = 0, rounds = 0;
+  int window_bits = 0, n_windows = 0, rounds = 0, shared_buckets = 0;
   unsigned long long n_adds = 0;
   int h2d[2] = {-1, -1};  // scalar upload, set by the entry point
 };
@@ -60,6 +60,11 @@ struct msm_b200_ctx {
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
+  // window tables of the resident bases (shared-bucket mode, see k_build_table): table k = 2^(k * table_c) G
+  int table_c = 0, table_K = 0;      // 0: no tables
+  bool tables_enabled = true;        // MSM_B200_TABLES=0 disables
+  int table_max_log2n = 21;          // largest point set that gets tables (MSM_B200_TABLE_MAX_LOG2N; measured:
+                                     // 2^21 -2.6 %, 2^22 +-0: the denser histogram atomics eat the gain)
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
   DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others, tilesum;
@@ -169,6 +174,7 @@ static int resolve_timing(msm_b200_ctx* ctx, msm_b200_timing* tm) {
   const PendingTiming& pt = ctx->pending;
   tm->window_bits = pt.window_bits;
   tm->n_windows = pt.n_windows;
+  tm->shared_buckets = pt.shared_buckets;
   if (!pt.valid) return 0;  // nothing was launched (empty input, all-zero scalars, digit dump)
   CK(cudaStreamSynchronize(ctx->stream));
   Timer T(ctx);
@@ -219,16 +225,32 @@ static int default_window(int curve, int form, size_t n) {
 // ------------------------------------------------------------------------------------------
 // set_bases
 // ------------------------------------------------------------------------------------------
-template <class F>
-static int ingest_weierstrass(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout) {
-  RET_IF(ensure(ctx, ctx->bases, n * 2 * (2 * F::N * 4)));
+// `tables`: also build the window tables 2^(kc) G (resident bases only; the one-shot call passes false -- the
+// tables cost about three MSMs to build)
+template <class F, class G, uint32_t B3>
+static int ingest_weierstrass(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout, bool tables) {
+  constexpr size_t REC = 2 * F::N * 4;  // bytes per record (x | y); two records per point
+  ctx->table_c = ctx->table_K = 0;
+  const int c = default_window(ctx->curve, MSM_FORM_AFFINE_GLV, n);
+  const int K = (G::MAXBITS + 1 + c - 1) / c;
+  tables = tables && ctx->tables_enabled && c >= 12 && ceil_log2_sz(n) <= ctx->table_max_log2n &&
+           (unsigned long long)2 * n * K < (1ull << 31);
+  RET_IF(ensure(ctx, ctx->bases, n * 2 * REC * (tables ? K : 1)));
   LAUNCH(ctx, k_ingest_points<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
+  if (tables) {
+    for (int k = 1; k < K; k++)
+      LAUNCH(ctx, (k_build_table<F, B3>), cdiv(n, 256), 256, (const uint4*)((const char*)ctx->bases.p + (size_t)(k - 1) * n * 2 * REC),
+             (uint4*)((char*)ctx->bases.p + (size_t)k * n * 2 * REC), n, c);
+    ctx->table_c = c;
+    ctx->table_K = K;
+  }
   CK(cudaGetLastError());
   return 0;
 }
 
 template <class F>
-static int ingest_te(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout) {
+static int ingest_te(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout, bool tables) {
+  (void)tables;
   RET_IF(ensure(ctx, ctx->bases, n * (3 * F::N * 4)));
   LAUNCH(ctx, k_te_ingest<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
   CK(cudaGetLastError());
@@ -373,6 +395,8 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.ent = nullptr;
   sa.pairkey = nullptr;
   sa.digits = nullptr;
+  sa.bucket_stride = L;
+  sa.ent_stride = 0;
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
@@ -478,8 +502,14 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   ctx->pending.window_bits = c;
   ctx->pending.n_windows = K;
   const uint32_t L = 1u << (c - 1);
-  const size_t NB = (size_t)K * L;
+  // shared buckets: the resident bases carry a table 2^(kc) G per window, so all windows add into ONE set
+  // of L buckets (no Horner step, K times fewer buckets to reduce); the digit dump of the tests keeps the
+  // classic layout
+  const bool shared = ctx->table_c == c && ctx->table_K == K && !digits_dump_dev;
+  const int KR = shared ? 1 : K;  // bucket sets to reduce
+  const size_t NB = (size_t)KR * L;
   const size_t S = 2 * n;
+  ctx->pending.shared_buckets = shared ? 1 : 0;
   if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
   // sorted-entry slots are addressed with 32 bits (2 * pair offset + position)
   if ((unsigned long long)S * K >= (1ull << 31))
@@ -507,6 +537,8 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   sa.ent = nullptr;
   sa.pairkey = nullptr;
   sa.digits = digits_dump_dev;
+  sa.bucket_stride = shared ? 0u : L;
+  sa.ent_stride = shared ? (uint32_t)(2 * ctx->n_bases) : 0u;
   LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
   int e1 = T.mark();
   // --- offsets for every round; the host needs the totals (one sync), the scatter does not: it is queued
@@ -603,7 +635,10 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     if (((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)ctx->finish_max_elems &&
         (double)adds_left * (ctx->finish_add_modmuls - 6.0) <= (double)(R - r) * ctx->finish_round_modmuls) {
       RET_IF(ensure(ctx, ctx->buckets, NB * 3 * FE));
-      if (r == 0) {
+      if (2 * P >= 3 * NB) {  // dense buckets (3+ elements each on average): one thread per bucket
+        if (r == 0) LAUNCH(ctx, (k_finish_buckets<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+        else LAUNCH(ctx, (k_finish_buckets<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+      } else if (r == 0) {
         LAUNCH(ctx, (k_finish_slots<F, B3, true>), cdiv(P, 64), 64, a, (uint4*)ctx->buckets.p);
         LAUNCH(ctx, (k_finish_rest<F, true>), cdiv(NB, 128), 128, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
       } else {
@@ -675,13 +710,13 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   if (finished_projective) {
     AccBucketLoader<WeierCurve<F, B3>> ld;
     ld.buckets = (const uint4*)ctx->buckets.p;
-    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
+    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, KR, c)));
   } else {
     AffineBucketLoader<F, B3> ld;
     ld.fin = (const uint4*)ctx->fin.p;
     ld.cap = NB;
     ld.cnt = (const uint32_t*)ctx->cnt.p;
-    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, K, c)));
+    RET_IF((reduce_buckets<WeierCurve<F, B3>>(ctx, ld, NB, KR, c)));
   }
   int e4 = T.mark();
   {
@@ -703,7 +738,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
 // per-curve entry points (one translation unit each, so the curves build in parallel)
 // ------------------------------------------------------------------------------------------
 struct CurveOps {
-  int (*ingest)(msm_b200_ctx*, const void* d_in, size_t n, int layout);
+  int (*ingest)(msm_b200_ctx*, const void* d_in, size_t n, int layout, bool tables);
   int (*run)(msm_b200_ctx*, const void* d_scalars, size_t n, int layout, int form, int c, msm_b200_timing*,
              uint32_t* digits_dump_dev);
   int (*zero_partial)(msm_b200_ctx*);
@@ -742,7 +777,7 @@ static int run_weierstrass_t(msm_b200_ctx* ctx, const void* d_s, size_t n, int l
 
 #define MSM_DEFINE_WEIERSTRASS_CURVE(fn, F, G, B3)                                                          \
   const CurveOps* fn() {                                                                                    \
-    static const CurveOps ops = {ingest_weierstrass<F>,          run_weierstrass_t<F, G, B3>,                \
+    static const CurveOps ops = {ingest_weierstrass<F, G, B3>,   run_weierstrass_t<F, G, B3>,                \
                                  zero_partial_t<WeierCurve<F, B3>>, finalize_any<WeierCurve<F, B3>>,         \
                                  random_points_t<WeierCurve<F, B3>, G>, random_scalars_t<G>};                \
     return &ops;                                                                                            \

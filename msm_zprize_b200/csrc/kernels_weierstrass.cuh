@@ -159,6 +159,11 @@ struct SortArgs {
   uint32_t* ent;        // sorted entries, 2 * P0 slots
   uint32_t* pairkey;    // bucket of every round-0 pair
   uint32_t* digits;     // optional dump (tests): S*K
+  // window k adds into buckets [k * bucket_stride, ...) and its entries point at base record
+  // k * ent_stride + h.  Classic layout: (L, 0).  Shared buckets (precomputed 2^(kc) G tables, one
+  // record set per window): (0, records per table) -- every window adds into the same L buckets.
+  uint32_t bucket_stride;
+  uint32_t ent_stride;
 };
 
 template <bool SCATTER>
@@ -173,13 +178,13 @@ __global__ void k_hist_scatter(SortArgs a) {
     uint32_t l = signed_digit<4>(s, k, a.c, carry);
     if (a.digits && !SCATTER) a.digits[h * a.K + k] = l | ((l ? (carry ^ sign) : 0u) << 31);
     if (l == 0) continue;
-    uint32_t b = (uint32_t)k * a.L + (l - 1);
+    uint32_t b = (uint32_t)k * a.bucket_stride + (l - 1);
     if (!SCATTER) {
       atomicAdd(&a.cnt[b], 1u);
     } else {
       uint32_t pos = atomicAdd(&a.cursor[b], 1u);
       uint32_t slot = 2u * a.po0[b] + pos;
-      a.ent[slot] = (uint32_t)h | ((carry ^ sign) << 31);  // (pairkey is filled by k_fill_pairkey)
+      a.ent[slot] = ((uint32_t)h + (uint32_t)k * a.ent_stride) | ((carry ^ sign) << 31);  // (pairkey: k_fill_pairkey)
     }
   }
 }
@@ -671,6 +676,82 @@ __global__ void __launch_bounds__(128) k_finish_rest(RoundArgs<F> a, uint32_t NB
   st_aos<F>(o, acc.X);
   st_aos<F>(o + F::N / 4, acc.Y);
   st_aos<F>(o + 2 * F::N / 4, acc.Z);
+}
+
+// Same tail with one thread per BUCKET, for dense buckets (shared-bucket mode: every bucket still has
+// 2^k elements when the tree stops, so slot-indexed threads would leave most lanes of a warp idle).
+template <class F, uint32_t B3, bool R0>
+__global__ void __launch_bounds__(64) k_finish_buckets(RoundArgs<F> a, uint32_t NB, uint4* __restrict__ buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  const uint32_t cnt = a.cnt[b];
+  const uint32_t n = (uint32_t)(((unsigned long long)cnt + (1ull << a.r) - 1) >> a.r);
+  Proj<F> acc;
+  if (cnt == 0) {
+    acc = proj_zero<F>();
+  } else if (!R0 && n == 1) {
+    acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
+  } else {
+    const size_t e0 = 2 * (size_t)a.po_r[b];
+    acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0));
+#pragma unroll 1
+    for (uint32_t j = 1; j < n; j++) {
+      Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
+      if (aff_is_inf(Q)) continue;
+      if constexpr (F::LAZY && B3 == 3) acc = proj_add_mixed_nr<F>(acc, Q);
+      else acc = proj_add_mixed<F, B3>(acc, Q);
+    }
+    if constexpr (F::LAZY && B3 == 3) acc = proj_canon(acc);
+  }
+  uint4* o = buckets + (size_t)b * (3 * F::N / 4);
+  st_aos<F>(o, acc.X);
+  st_aos<F>(o + F::N / 4, acc.Y);
+  st_aos<F>(o + 2 * F::N / 4, acc.Z);
+}
+
+// Window tables for RESIDENT bases (built once per point set by set_bases): table k holds 2^(kc) G_i and
+// its endomorphism image for every base point, so that the digits of ALL windows can be added into ONE
+// set of 2^(c-1) buckets -- the bucket reduction then runs over L instead of K L buckets and the Horner
+// combination of the windows (K - 1) c dependent doublings in one warp) disappears.  One thread per
+// point: c projective doublings of the previous table's point, one inversion per block (product of the
+// block's Z values, block_products), affine records out.  The reference has no counterpart (its points are
+// copied and sign-folded on every call, src/msm-batched-affine.ts:338-409); the sum is the same group
+// element.
+template <class F, uint32_t B3>
+__global__ void __launch_bounds__(256) k_build_table(const uint4* __restrict__ prev, uint4* __restrict__ next, size_t n, int c) {
+  __shared__ uint32_t smem[97 * F::N + F::N];
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const bool valid = i < n;
+  Aff<F> P = aff_inf<F>();
+  if (valid) {
+    const uint4* r = prev + i * (size_t)(4 * F::N / 4);
+    P.x = ld_aos<F>(r);
+    P.y = ld_aos<F>(r + F::N / 4);
+  }
+  Proj<F> A = proj_from_aff(P);
+#pragma unroll 1
+  for (int d = 0; d < c; d++) A = proj_dbl<F, B3>(A);
+  const bool inf = fe_is_zero(A.Z);
+  Fe<F> others, total;
+  block_products<F, 256>(inf ? fe_one<F>() : A.Z, others, total, smem);
+  uint32_t* binv = smem + 97 * F::N;
+  __syncthreads();
+  if (threadIdx.x == 0) fe_to_smem<F>(binv, fe_inv(total));
+  __syncthreads();
+  if (!valid) return;
+  Aff<F> Q = aff_inf<F>(), E = Q;
+  if (!inf) {
+    const Fe<F> zi = fe_mul(others, fe_from_smem<F>(binv));
+    Q.x = fe_mul(A.X, zi);
+    Q.y = fe_mul(A.Y, zi);
+    E.x = fe_mul(Q.x, fe_beta<F>());
+    E.y = Q.y;
+  }
+  uint4* o = next + i * (size_t)(4 * F::N / 4);
+  st_aos<F>(o, Q.x);
+  st_aos<F>(o + F::N / 4, Q.y);
+  st_aos<F>(o + 2 * F::N / 4, E.x);
+  st_aos<F>(o + 3 * F::N / 4, E.y);
 }
 
 // upper levels of the product tree: plain arrays of field elements

@@ -46,7 +46,7 @@ for lg in [int(s) for s in args.sizes.split(",")]:
                           "total_ms": round(t["total_ms"], 3), "digits": round(t["digits_ms"], 3),
                           "sort": round(t["sort_ms"], 3), "acc": round(t["accumulate_ms"], 3),
                           "hot": round(t["hot_kernel_ms"], 3), "reduce": round(t["reduce_ms"], 3),
-                          "launches": t["kernel_launches"], "Mpts/s": round(n / t["total_ms"] / 1e3, 2),
+                          "launches": t["kernel_launches"], "shared": t["shared_buckets"], "Mpts/s": round(n / t["total_ms"] / 1e3, 2),
                           "same_as_first_c": ok}), flush=True)
     eng.dev_free(d_pts)
     eng.dev_free(d_sc)
