@@ -166,7 +166,7 @@ def w_alg(curve, n, c, te=False, shared_buckets=False):
     S = n if te else 2 * n
     if shared_buckets:  # every window adds into ONE set of L buckets (precomputed 2^(kc) G tables)
         A = S * K * (1 - 2.0 ** -c) - L * (1 - math.exp(-S * K / L))
-        return (6 * A + 25 * L + n) * lp
+        return (8 * A + 18 * L) * lp if te else (6 * A + 25 * L + n) * lp
     A = S * K * (1 - 2.0 ** -c) - K * L * (1 - math.exp(-S / L))
     if te:
         return (8 * A + 18 * K * L) * lp
@@ -387,8 +387,9 @@ def strong_case(g, curve, T, steps, peak_lp):
     med, sd = med_sd(ms)
     med = max_over_ranks(g, med)
     out.update({"ms": med, "ms_sd": sd, "mpoints_s": (1 << T) / (med * 1e-3) / 1e6, "window_bits": tm["window_bits"],
-                "whole_msm_frac_per_gpu": w_alg(curve, 1 << (T - lw), tm["window_bits"], te) / (med * 1e-3) / peak_lp
-                if peak_lp else None})
+                "shared_buckets": tm["shared_buckets"],
+                "whole_msm_frac_per_gpu": w_alg(curve, 1 << (T - lw), tm["window_bits"], te, bool(tm["shared_buckets"])) /
+                (med * 1e-3) / peak_lp if peak_lp else None})
     sh.close()
     if g.world > 1:
         single = None
@@ -585,6 +586,7 @@ def main():
         "scaling": "strong" if args.total_log2n else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "ok": ok, "notes": notes,
         "config": {"workload": workload_name(curve, args.log2n), "window_bits": c_used, "n_windows": K_used,
+                   "shared_buckets": shared,
                    "points_total": world * n, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": f"range-sharded x{world}" if world > 1 else "single GPU",
                    "statistic": "median of the timed steps (sample sd in ms_sd), max over ranks",

@@ -111,11 +111,12 @@ const char* msm_b200_global_error(void);
  * preparePointsAndScalars does per point (copy, endomorphism; src/msm-batched-affine.ts:338-409)
  * and, for LE_BYTES, what Parallel.pointsFromBytes does (src/parallel.ts:97-116,209-232).
  * `points` is host memory unless `on_device` != 0.
- * For GLV curves with 2^14 <= n <= 2^21 points this call also builds the window tables 2^(kc) G_i of the set
- * (K - 1 more record sets in device memory, about three MSMs of work, once): later msm_b200_run calls with the
- * default window then add the digits of all windows into one shared set of buckets (timing.shared_buckets = 1;
- * same point, shorter bucket reduction, no Horner step).  MSM_B200_TABLES=0 in the environment turns this off;
- * the one-shot msm_b200_msm never builds tables. */
+ * For 2^14 <= n <= 2^25 points (2^13 for twisted Edwards) this call also builds the window tables 2^(kc) G_i of
+ * the set (K - 1 more record sets in device memory, about three MSMs of work, once): later msm_b200_run calls
+ * with the default window then add the digits of all windows into one shared set of buckets
+ * (timing.shared_buckets = 1; same point; K times fewer buckets to reduce, no Horner step, and wider windows --
+ * fewer additions -- pay earlier).  MSM_B200_TABLES=0 in the environment turns this off; an explicit window_bits
+ * other than the tables' and the one-shot msm_b200_msm use the classic layout (one bucket set per window). */
 int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device);
 /* Same for host points, without waiting: the copy and the ingest kernel are queued on the context's copy
  * stream and the next run / run_partial waits for them only where it first reads a base point, i.e. behind its

@@ -76,6 +76,9 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
     return fail(ctx, MSM_E_INVALID, "Weierstrass curve needs MSM_FORM_AFFINE_GLV or MSM_FORM_PROJECTIVE");
   CK(cudaSetDevice(ctx->device));
   int c = window_bits > 0 ? window_bits : default_window(ctx->curve, form, n ? n : 1);
+  // resident bases with window tables: the tables' window size is the default (shared buckets)
+  // (the same for the GLV form of the Weierstrass curves)
+  if (window_bits <= 0 && ctx->table_c > 0 && n >= ((size_t)1 << 12) && (te || form == MSM_FORM_AFFINE_GLV)) c = ctx->table_c;
   if (c < 1 || c > 24) return fail(ctx, MSM_E_INVALID, "window_bits out of range [1,24]");
   Timer T(ctx);
   int t0 = T.mark();
@@ -182,7 +185,9 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = std::min(std::max(1, atoi(e)), (int)ACC_MAX_PAIRS);
   if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = std::min(std::max(1, atoi(e)), 5);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = std::min(std::max(1, atoi(e)), 5);
+  if (const char* e = getenv("MSM_B200_REDUCE_Q0")) ctx->reduce_quad0 = atoi(e) != 0;
   if (const char* e = getenv("MSM_B200_TABLES")) ctx->tables_enabled = atoi(e) != 0;
+  if (const char* e = getenv("MSM_B200_TABLE_WINDOW")) ctx->table_window = std::min(std::max(0, atoi(e)), 24);
   if (const char* e = getenv("MSM_B200_TABLE_MAX_LOG2N")) ctx->table_max_log2n = std::min(std::max(0, atoi(e)), 26);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)std::max(1ll, atoll(e));
   if (stream) {

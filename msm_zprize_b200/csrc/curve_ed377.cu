@@ -10,7 +10,7 @@ static int run_te(msm_b200_ctx* ctx, const void* d_s, size_t n, int layout, int 
 }
 
 const CurveOps* curve_ops_ed377() {
-  static const CurveOps ops = {ingest_te<Bls377Fr>,
+  static const CurveOps ops = {ingest_te<Bls377Fr, EdScalar>,
                                run_te,
                                zero_partial_t<TeCurve<Bls377Fr>>,
                                finalize_any<TeCurve<Bls377Fr>>,

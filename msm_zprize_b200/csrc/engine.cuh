@@ -54,17 +54,22 @@ struct msm_b200_ctx {
   double finish_round_modmuls = 1.0e6;
   int finish_max_elems = FINISH_MAX_ELEMS;
   int acc_min_pairs = ACC_MIN_PAIRS;  // MSM_B200_ACC_MIN_PAIRS (tuning)
-  int reduce_gb0 = 3;          // MSM_B200_REDUCE_GB0 (tuning)
-  int reduce_warp_gb = 3;         // MSM_B200_REDUCE_WARP_GB (2^18 buckets: 5 -> 1.29 ms, 4 -> 1.25, 3 -> 1.22, 2 -> 1.24)
-  size_t reduce_warp_min = 4096;  // MSM_B200_REDUCE_WARP_MIN: levels with more items use one lane per item
+  // bits per level of the bucket reduction; 0 = by bucket count (reduce_buckets): 2^18 buckets: 8 buckets per
+  // thread at level 0, one item per lane while > 4096 items; <= 2^16 buckets (shared-bucket mode): level 0
+  // with one lane quad per 4 buckets, every further level quad-cooperative (tools/sweep_reduce.sh)
+  int reduce_gb0 = 0;          // MSM_B200_REDUCE_GB0 (tuning)
+  int reduce_warp_gb = 3;      // MSM_B200_REDUCE_WARP_GB (2^18 buckets: 5 -> 1.29 ms, 4 -> 1.25, 3 -> 1.22, 2 -> 1.24)
+  size_t reduce_warp_min = 0;  // MSM_B200_REDUCE_WARP_MIN: levels with more items use one lane per item
+  int reduce_quad0 = -1;       // MSM_B200_REDUCE_Q0: level 0 on lane quads (1) or lone lanes (0); -1 = by bucket count
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
   // window tables of the resident bases (shared-bucket mode, see k_build_table): table k = 2^(k * table_c) G
   int table_c = 0, table_K = 0;      // 0: no tables
   bool tables_enabled = true;        // MSM_B200_TABLES=0 disables
-  int table_max_log2n = 21;          // largest point set that gets tables (MSM_B200_TABLE_MAX_LOG2N; measured:
-                                     // 2^21 -2.6 %, 2^22 +-0: the denser histogram atomics eat the gain)
+  int table_max_log2n = 25;          // largest point set that gets tables (MSM_B200_TABLE_MAX_LOG2N): 2^26 points
+                                     // with 6 record sets + the workspace of the rounds exceed 180 GB
+  int table_window = 0;              // MSM_B200_TABLE_WINDOW: forces the tables' window size (tuning)
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
   DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others, tilesum;
@@ -225,15 +230,26 @@ static int default_window(int curve, int form, size_t n) {
 // ------------------------------------------------------------------------------------------
 // set_bases
 // ------------------------------------------------------------------------------------------
+// Window size for GLV bases WITH tables: all windows add into the same 2^(c-1) buckets, so the cost is
+// 2n * ceil(128 / c) additions plus ONE bucket reduction over 2^(c-1) buckets.  Only window sizes that cut the
+// window count matter: 16 (8 windows), 19 (7), 22 (6).  Measured crossovers (tools/sweep_tables.sh).
+static int glv_table_window(const msm_b200_ctx* ctx, size_t n) {
+  if (ctx->table_window > 0) return ctx->table_window;
+  int lg = ceil_log2_sz(n);
+  // BLS12-377: 2^21..2^23 -6 %, 2^24 -11 % against no tables; with 8-limb fields the scatter into 2^21 buckets
+  // costs more than the sixth window saves
+  return (lg >= 24 && field_is_large(ctx->curve)) ? 22 : (lg >= 21 ? 19 : 16);
+}
+
 // `tables`: also build the window tables 2^(kc) G (resident bases only; the one-shot call passes false -- the
 // tables cost about three MSMs to build)
 template <class F, class G, uint32_t B3>
 static int ingest_weierstrass(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout, bool tables) {
   constexpr size_t REC = 2 * F::N * 4;  // bytes per record (x | y); two records per point
   ctx->table_c = ctx->table_K = 0;
-  const int c = default_window(ctx->curve, MSM_FORM_AFFINE_GLV, n);
+  const int c = glv_table_window(ctx, n);
   const int K = (G::MAXBITS + 1 + c - 1) / c;
-  tables = tables && ctx->tables_enabled && c >= 12 && ceil_log2_sz(n) <= ctx->table_max_log2n &&
+  tables = tables && ctx->tables_enabled && ceil_log2_sz(n) >= 14 && ceil_log2_sz(n) <= ctx->table_max_log2n &&
            (unsigned long long)2 * n * K < (1ull << 31);
   RET_IF(ensure(ctx, ctx->bases, n * 2 * REC * (tables ? K : 1)));
   LAUNCH(ctx, k_ingest_points<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
@@ -248,11 +264,32 @@ static int ingest_weierstrass(msm_b200_ctx* ctx, const void* d_in, size_t n, int
   return 0;
 }
 
-template <class F>
+// Window size for twisted-Edwards bases WITH tables: every window adds into the same 2^(c-1) buckets, so the
+// cost is n * ceil(252 / c) additions plus a bucket reduction over 2^(c-1) buckets only -- wider windows pay
+// earlier than in the classic layout (c = 14, 18 bucket sets).
+static int te_table_window(const msm_b200_ctx* ctx, size_t n) {
+  if (ctx->table_window > 0) return ctx->table_window;
+  int lg = ceil_log2_sz(n);
+  return lg >= 19 ? 18 : (lg >= 17 ? 16 : 14);  // 2^22: 9.2 ms (c = 18) / 9.7 (20) / 10.3 (16) / 11.7 (no tables)
+}
+
+template <class F, class S>
 static int ingest_te(msm_b200_ctx* ctx, const void* d_in, size_t n, int layout, bool tables) {
-  (void)tables;
-  RET_IF(ensure(ctx, ctx->bases, n * (3 * F::N * 4)));
+  constexpr size_t REC = 3 * F::N * 4;  // bytes per cached point (y+x | y-x | 2dxy)
+  ctx->table_c = ctx->table_K = 0;
+  const int c = te_table_window(ctx, n);
+  const int K = (S::QBITS + 1 + c - 1) / c;
+  tables = tables && ctx->tables_enabled && ceil_log2_sz(n) >= 13 && ceil_log2_sz(n) <= ctx->table_max_log2n &&
+           (unsigned long long)n * K < (1ull << 31);
+  RET_IF(ensure(ctx, ctx->bases, n * REC * (tables ? K : 1)));
   LAUNCH(ctx, k_te_ingest<F>, cdiv(n, 128), 128, (const uint8_t*)d_in, n, layout, (uint4*)ctx->bases.p);
+  if (tables) {
+    for (int k = 1; k < K; k++)
+      LAUNCH(ctx, k_te_build_table<F>, cdiv(n, 256), 256, (const uint4*)((const char*)ctx->bases.p + (size_t)(k - 1) * n * REC),
+             (uint4*)((char*)ctx->bases.p + (size_t)k * n * REC), n, c);
+    ctx->table_c = c;
+    ctx->table_K = K;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -324,17 +361,21 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   constexpr size_t ITEM = (size_t)item_u4<C>() * 16;
   int remaining = c - 1;
   // level 0: 8 buckets per thread (measured best of 4 / 8 / 16 / 32 at 2^18 buckets: 1.59 / 1.28 / 1.44 / 1.94 ms
-  // for the whole reduction)
-  int gb0 = ctx->reduce_gb0;
+  // for the whole reduction); few buckets: 4 per lane quad
+  const bool few = NB <= ((size_t)1 << 16);
+  const int gb0 = ctx->reduce_gb0 > 0 ? ctx->reduce_gb0 : (few ? 2 : 3);
+  const size_t warp_min = ctx->reduce_warp_min > 0 ? ctx->reduce_warp_min : (few ? (size_t)1 << 16 : (size_t)4096);
+  const bool quad0 = ctx->reduce_quad0 >= 0 ? ctx->reduce_quad0 != 0 : few;
   int gb = remaining < gb0 ? remaining : gb0;
   size_t items = NB >> gb;
   RET_IF(ensure(ctx, ctx->red[0], items * ITEM));
   RET_IF(ensure(ctx, ctx->red[1], (items / 2 + 1) * ITEM));
-  LAUNCH(ctx, (k_reduce0<C, Loader>), cdiv(items, 64), 64, ld, (uint32_t)NB, gb, (uint4*)ctx->red[0].p);
+  if (quad0) LAUNCH(ctx, (k_reduce0_quad<C, Loader>), cdiv(items * 4, 64), 64, ld, (uint32_t)NB, gb, (uint4*)ctx->red[0].p);
+  else LAUNCH(ctx, (k_reduce0<C, Loader>), cdiv(items, 64), 64, ld, (uint32_t)NB, gb, (uint4*)ctx->red[0].p);
   remaining -= gb;
   int cur = 0;
   while (remaining > 0) {
-    if (items > ctx->reduce_warp_min) {
+    if (items > warp_min) {
       gb = remaining < ctx->reduce_warp_gb ? remaining : ctx->reduce_warp_gb;  // one item per lane, groups of 2^gb lanes
       LAUNCH(ctx, (k_reduce_warp<C>), cdiv(items, 64), 64, (const uint4*)ctx->red[cur].p, (uint32_t)items, gb,
              (uint4*)ctx->red[cur ^ 1].p);
@@ -369,7 +410,12 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   ctx->pending.window_bits = c;
   ctx->pending.n_windows = K;
   const uint32_t L = 1u << (c - 1);
-  const size_t NB = (size_t)K * L;
+  // shared buckets: the resident bases carry one table 2^(kc) P per window (twisted Edwards: k_te_build_table);
+  // the Weierstrass tables are laid out for the GLV half scalars and only match here if K does
+  const bool shared = C::BASE_STRIDE == 1 && ctx->table_c == c && ctx->table_K == K;
+  const int KR = shared ? 1 : K;
+  const size_t NB = (size_t)KR * L;
+  ctx->pending.shared_buckets = shared ? 1 : 0;
   if (NB > ((size_t)1 << 28)) return fail(ctx, MSM_E_INVALID, "window too large");
   // sorted-entry slots are addressed with 32 bits (2 * pair offset + position)
   if ((unsigned long long)n * K >= (1ull << 31))
@@ -395,8 +441,8 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.ent = nullptr;
   sa.pairkey = nullptr;
   sa.digits = nullptr;
-  sa.bucket_stride = L;
-  sa.ent_stride = 0;
+  sa.bucket_stride = shared ? 0u : L;
+  sa.ent_stride = shared ? (uint32_t)ctx->n_bases : 0u;
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
@@ -443,7 +489,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   int e3 = T.mark();
   AccBucketLoader<C> ld;
   ld.buckets = (const uint4*)ctx->buckets.p;
-  RET_IF((reduce_buckets<C>(ctx, ld, NB, K, c)));
+  RET_IF((reduce_buckets<C>(ctx, ld, NB, KR, c)));
   int e4 = T.mark();
   {
     PendingTiming& pt = ctx->pending;

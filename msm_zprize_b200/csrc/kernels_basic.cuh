@@ -38,6 +38,41 @@ __global__ void k_te_ingest(const uint8_t* __restrict__ in, size_t n, int layout
   st_aos<F>(o + 2 * F::N / 4, q.kt);
 }
 
+// Window tables for resident twisted-Edwards bases (see k_build_table in kernels_weierstrass.cuh): table k
+// holds 2^(kc) P_i in the cached form (y+x, y-x, 2dxy).  One thread per point: the previous table's point as
+// the extended point (4x : 4y : 4 : 4xy) -- no halving needed -- c doublings, one inversion per block.
+template <class F>
+__global__ void __launch_bounds__(256) k_te_build_table(const uint4* __restrict__ prev, uint4* __restrict__ next, size_t n, int c) {
+  __shared__ uint32_t smem[97 * F::N + F::N];
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const bool valid = i < n;
+  Ext<F> A = ext_zero<F>();
+  if (valid) {
+    const uint4* r = prev + i * (size_t)(3 * F::N / 4);
+    const Fe<F> yp = ld_aos<F>(r), ym = ld_aos<F>(r + F::N / 4);
+    const Fe<F> dx = fe_sub(yp, ym), sy = fe_add(yp, ym);  // 2x, 2y
+    A.X = fe_dbl(dx);
+    A.Y = fe_dbl(sy);
+    A.Z = fe_dbl(fe_dbl(fe_one<F>()));
+    A.T = fe_mul(dx, sy);
+  }
+#pragma unroll 1
+  for (int d = 0; d < c; d++) A = ext_dbl<F>(A);
+  Fe<F> others, total;
+  block_products<F, 256>(A.Z, others, total, smem);  // Z != 0 on a complete Edwards curve
+  uint32_t* binv = smem + 97 * F::N;
+  __syncthreads();
+  if (threadIdx.x == 0) fe_to_smem<F>(binv, fe_inv(total));
+  __syncthreads();
+  if (!valid) return;
+  const Fe<F> zi = fe_mul(others, fe_from_smem<F>(binv));
+  Niels<F> q = niels_from_xy(fe_mul(A.X, zi), fe_mul(A.Y, zi));
+  uint4* o = next + i * (size_t)(3 * F::N / 4);
+  st_aos<F>(o, q.yp);
+  st_aos<F>(o + F::N / 4, q.ym);
+  st_aos<F>(o + 2 * F::N / 4, q.kt);
+}
+
 // scalars -> 8 limbs in [0, q), two uint4 per scalar
 template <class S>
 __global__ void k_load_scalars(const uint8_t* __restrict__ in, size_t n, int layout, uint4* __restrict__ out) {
@@ -60,12 +95,12 @@ __global__ void k_hist_scatter8(SortArgs a) {
   for (int k = 0; k < a.K; k++) {
     uint32_t l = signed_digit<8>(s, k, a.c, carry);
     if (l == 0) continue;
-    uint32_t b = (uint32_t)k * a.L + (l - 1);
+    uint32_t b = (uint32_t)k * a.bucket_stride + (l - 1);
     if (!SCATTER) {
       atomicAdd(&a.cnt[b], 1u);
     } else {
       uint32_t pos = atomicAdd(&a.cursor[b], 1u);
-      a.ent[2u * a.po0[b] + pos] = (uint32_t)h | (carry << 31);
+      a.ent[2u * a.po0[b] + pos] = ((uint32_t)h + (uint32_t)k * a.ent_stride) | (carry << 31);
     }
   }
 }

@@ -334,6 +334,13 @@ struct AffineBucketLoader {
     if constexpr (F::LAZY && B3 == 3) run = proj_add_mixed_nr<F>(run, A);
     else run = proj_add_mixed<F, B3>(run, A);
   }
+  __device__ __forceinline__ Proj<F> load(uint32_t b) const {  // the bucket sum itself (neutral element if empty)
+    if (cnt[b] == 0) return proj_zero<F>();
+    Aff<F> A;
+    A.x = ld_soa<F>(fin, cap, b);
+    A.y = ld_soa<F>(fin + (size_t)(F::N / 4) * cap, cap, b);
+    return proj_from_aff(A);
+  }
 };
 
 // accumulators written by k_bucket_acc (basic bucket method)
@@ -342,6 +349,9 @@ struct AccBucketLoader {
   const uint4* buckets;
   __device__ __forceinline__ void add_bucket(typename C::Acc& run, uint32_t b) const {
     run = C::add(run, C::ld(buckets + (size_t)b * (C::ACC_FE * C::F::N / 4)));
+  }
+  __device__ __forceinline__ typename C::Acc load(uint32_t b) const {
+    return C::ld(buckets + (size_t)b * (C::ACC_FE * C::F::N / 4));
   }
 };
 
@@ -370,6 +380,31 @@ __global__ void __launch_bounds__(64) k_reduce0(Loader ld, uint32_t NB, int gb, 
   uint4* o = out + (size_t)u * item_u4<C>();
   C::st(o, run);
   C::st(o + item_u4<C>() / 2, tri);
+}
+
+// Level 0 with one group per lane QUAD (the four lanes share the field products of every addition): for few
+// buckets (shared-bucket mode, 2^15 of them) the level is bound by the latency of its 2 g dependent
+// additions, not by throughput, and a quad-cooperative addition takes about half the time of a lone lane's.
+template <class C, class Loader>
+__global__ void __launch_bounds__(64) k_reduce0_quad(Loader ld, uint32_t NB, int gb, uint4* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t u = t >> 2;
+  const uint32_t g = 1u << gb;
+  const bool live = (size_t)u * g < NB;  // NB is a multiple of g; dead quads only exist in the last warp
+  typename C::Acc run = C::zero(), tri = C::zero();
+#pragma unroll 1
+  for (int jj = (int)g - 1; jj >= 0; jj--) {
+    typename C::Acc B = live ? ld.load(u * g + jj) : C::zero();
+    run = C::addq(run, B);
+    tri = C::addq(tri, run);
+  }
+#pragma unroll 1
+  for (int d = 0; d < gb; d++) run = C::dblq(run);
+  if (live && (t & 3) == 0) {
+    uint4* o = out + (size_t)u * item_u4<C>();
+    C::st(o, run);
+    C::st(o + item_u4<C>() / 2, tri);
+  }
 }
 
 // Levels >= 1 with one item per lane: groups of g = 2^gb consecutive lanes (g <= 32).

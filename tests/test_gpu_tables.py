@@ -120,3 +120,61 @@ def test_shared_buckets_skewed_scalars(mz):
         assert (r.x, r.y, r.is_zero) == _port_msm(name, sc, pts, n)
         z = eng.run(bytes(32 * n), n)
         assert z.is_zero
+
+
+@pytest.mark.parametrize("lg,c_tab", [(13, 14), (17, 16)])
+def test_te_shared_buckets_equal_classic_and_port(mz, lg, c_tab):
+    """ed-on-bls12-377 (generic bucket method, src/msm-basic.ts): resident bases get tables 2^(kc) P in the cached
+    (y+x, y-x, 2dxy) form and the window size that goes with them."""
+    from oracle.port import Port
+    name = "ed-on-bls12-377"
+    n = (1 << lg) - 77
+    port = Port(name)
+    pts = port.random_points(n, 0x7E0 + lg, 8)
+    sc = port.random_scalars(n, 0x7E1 + lg, 8)
+    want = _port_msm(name, sc, pts, n)
+    with mz.MsmEngine(name) as eng:
+        eng.set_bases(pts, n)
+        a = eng.run(sc, n)
+        assert a.timing["shared_buckets"] == 1 and a.timing["window_bits"] == c_tab
+        assert (a.x, a.y, a.is_zero) == want
+        b = eng.run(sc, n, window_bits=11)  # classic layout over the same resident bases
+        assert b.timing["shared_buckets"] == 0 and (b.x, b.y, b.is_zero) == want
+        one = eng.msm(sc, pts, n)
+        assert one.timing["shared_buckets"] == 0 and (one.x, one.y, one.is_zero) == want
+        eng.set_bases(pts, n)
+        k = n - 1000
+        p = eng.run(sc, k)
+        assert p.timing["shared_buckets"] == 1 and (p.x, p.y, p.is_zero) == _port_msm(name, sc[:32 * k], pts[:64 * k], k)
+
+
+def test_te_shared_buckets_special_inputs(mz):
+    """Unified additions under the tables: repeated points, P / -P pairs, the neutral point (0, 1) as an input,
+    scalars 0 / 1 / q - 1, and all-equal scalars (a few buckets hold everything: virtual-bucket split + tree)."""
+    name = "ed-on-bls12-377"
+    te = O.TwistedEdwards(O.ED_ON_BLS12_377)
+    from oracle.port import Port
+    port = Port(name)
+    n = 1 << 13
+    base = port.random_points(n, 0x7ED, 8)
+    P = [(int.from_bytes(base[64 * i:64 * i + 32], "little"), int.from_bytes(base[64 * i + 32:64 * i + 64], "little"))
+         for i in range(n)]
+    rng = random.Random(7)
+    sc = [rng.randrange(te.q) for _ in range(n)]
+    for i in range(64):
+        P[i], sc[i] = P[0], sc[0]
+    for i in range(100, 200, 2):
+        P[i + 1] = te.to_affine(te.negate(te.from_affine(P[i])))
+        sc[i + 1] = sc[i]
+    P[250] = (0, 1)
+    sc[300], sc[301], sc[302] = 0, 1, te.q - 1
+    pts_le, sc_le = I.points_le(P, 32), I.scalars_le(sc)
+    with mz.MsmEngine(name) as eng:
+        eng.set_bases(pts_le, n)
+        r = eng.run(sc_le, n)
+        assert r.timing["shared_buckets"] == 1 and (r.x, r.y, r.is_zero) == _port_msm(name, sc_le, pts_le, n)
+        same = I.scalars_le([sc[5]] * n)
+        r = eng.run(same, n)
+        assert r.timing["shared_buckets"] == 1 and (r.x, r.y, r.is_zero) == _port_msm(name, same, pts_le, n)
+        z = eng.run(bytes(32 * n), n)
+        assert z.is_zero and (z.x, z.y) == (0, 1)
