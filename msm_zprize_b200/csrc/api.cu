@@ -180,7 +180,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   // development knobs (launch shapes only, never results); out-of-range values are clamped to what the
   // kernels support: group bits 1..5 (a group must fit a warp), at least one pair / element
   if (const char* e = getenv("MSM_B200_FINISH_ADD")) ctx->finish_add_modmuls = std::max(6.0, atof(e));
-  if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = std::max(0.0, atof(e));
+  if (const char* e = getenv("MSM_B200_FINISH_ROUND")) ctx->finish_round_modmuls = std::max(1.0, atof(e));
   if (const char* e = getenv("MSM_B200_FINISH_ELEMS")) ctx->finish_max_elems = std::max(1, atoi(e));
   if (const char* e = getenv("MSM_B200_ACC_MIN_PAIRS")) ctx->acc_min_pairs = std::min(std::max(1, atoi(e)), (int)ACC_MAX_PAIRS);
   if (const char* e = getenv("MSM_B200_REDUCE_GB0")) ctx->reduce_gb0 = std::min(std::max(1, atoi(e)), 5);

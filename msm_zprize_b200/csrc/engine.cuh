@@ -51,8 +51,8 @@ struct msm_b200_ctx {
   int sm_count = 148;
   // cost model of the tree tail (run_affine_glv); MSM_B200_FINISH_ADD / MSM_B200_FINISH_ROUND override (tuning)
   double finish_add_modmuls = 18.0;
-  double finish_round_modmuls = 1.0e6;
-  int finish_max_elems = FINISH_MAX_ELEMS;
+  double finish_round_modmuls = 0;  // 0: 1e6 (classic layout, slot-indexed tail) / 3e6 (shared buckets, dense tail)
+  int finish_max_elems = 0;         // 0: 16 / 32 elements per bucket at most when the tail takes over
   int acc_min_pairs = ACC_MIN_PAIRS;  // MSM_B200_ACC_MIN_PAIRS (tuning)
   // bits per level of the bucket reduction; 0 = by bucket count (reduce_buckets): 2^18 buckets: 8 buckets per
   // thread at level 0, one item per lane while > 4096 items; <= 2^16 buckets (shared-bucket mode): level 0
@@ -678,12 +678,14 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     // divergence of a thread-per-bucket loop).  Only with few elements per bucket (serial chain).
     unsigned long long adds_left = 0;
     for (int s = r; s < R; s++) adds_left += ctx->h_totals[MAX_ROUNDS + 3 + s];
-    if (((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)ctx->finish_max_elems &&
-        (double)adds_left * (ctx->finish_add_modmuls - 6.0) <= (double)(R - r) * ctx->finish_round_modmuls) {
+    const int fin_elems = ctx->finish_max_elems > 0 ? ctx->finish_max_elems : (shared ? 2 * FINISH_MAX_ELEMS : FINISH_MAX_ELEMS);
+    const double fin_round = ctx->finish_round_modmuls > 0 ? ctx->finish_round_modmuls : (shared ? 3.0e6 : 1.0e6);
+    if (((maxcnt + (1ull << r) - 1) >> r) <= (unsigned long long)fin_elems &&
+        (double)adds_left * (ctx->finish_add_modmuls - 6.0) <= (double)(R - r) * fin_round) {
       RET_IF(ensure(ctx, ctx->buckets, NB * 3 * FE));
       if (2 * P >= 3 * NB) {  // dense buckets (3+ elements each on average): one thread per bucket
-        if (r == 0) LAUNCH(ctx, (k_finish_buckets<F, B3, true>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
-        else LAUNCH(ctx, (k_finish_buckets<F, B3, false>), cdiv(NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+        if (r == 0) LAUNCH(ctx, (k_finish_buckets<F, B3, true>), cdiv(2 * NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
+        else LAUNCH(ctx, (k_finish_buckets<F, B3, false>), cdiv(2 * NB, 64), 64, a, (uint32_t)NB, (uint4*)ctx->buckets.p);
       } else if (r == 0) {
         LAUNCH(ctx, (k_finish_slots<F, B3, true>), cdiv(P, 64), 64, a, (uint4*)ctx->buckets.p);
         LAUNCH(ctx, (k_finish_rest<F, true>), cdiv(NB, 128), 128, a, (uint32_t)NB, (uint4*)ctx->buckets.p);

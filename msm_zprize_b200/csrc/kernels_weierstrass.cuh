@@ -678,31 +678,44 @@ __global__ void __launch_bounds__(128) k_finish_rest(RoundArgs<F> a, uint32_t NB
   st_aos<F>(o + 2 * F::N / 4, acc.Z);
 }
 
-// Same tail with one thread per BUCKET, for dense buckets (shared-bucket mode: every bucket still has
-// 2^k elements when the tree stops, so slot-indexed threads would leave most lanes of a warp idle).
+// Same tail for dense buckets (shared-bucket mode: every bucket still has ~2^k elements when the tree stops,
+// so slot-indexed threads would leave most lanes of a warp idle): TWO adjacent lanes per bucket, each sums
+// half of the bucket's elements with mixed additions, then one complete addition joins the halves (the serial
+// chain is half as long and twice as many warps hide its latency: 210 -> ~120 us for 2^15 buckets of ~8).
 template <class F, uint32_t B3, bool R0>
 __global__ void __launch_bounds__(64) k_finish_buckets(RoundArgs<F> a, uint32_t NB, uint4* __restrict__ buckets) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= NB) return;
-  const uint32_t cnt = a.cnt[b];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t b = t >> 1, half = t & 1u;
+  const bool live = b < NB;  // both lanes of a pair are live or dead together
+  const uint32_t cnt = live ? a.cnt[b] : 0u;
   const uint32_t n = (uint32_t)(((unsigned long long)cnt + (1ull << a.r) - 1) >> a.r);
-  Proj<F> acc;
-  if (cnt == 0) {
-    acc = proj_zero<F>();
-  } else if (!R0 && n == 1) {
-    acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
-  } else {
+  Proj<F> acc = proj_zero<F>();
+  if (cnt != 0 && !R0 && n == 1) {
+    if (half == 0) acc = proj_from_aff(a.fin.load(b));  // finished in an earlier round
+  } else if (cnt != 0) {
     const size_t e0 = 2 * (size_t)a.po_r[b];
-    acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0]) : a.in.load(e0));
+    const uint32_t mid = (n + 1) >> 1;
+    const uint32_t lo = half ? mid : 0u, hi = half ? n : mid;
+    if (lo < hi) acc = proj_from_aff(R0 ? gather_base<F>(a.bases, a.ent[e0 + lo]) : a.in.load(e0 + lo));
 #pragma unroll 1
-    for (uint32_t j = 1; j < n; j++) {
+    for (uint32_t j = lo + 1; j < hi; j++) {
       Aff<F> Q = R0 ? gather_base<F>(a.bases, a.ent[e0 + j]) : a.in.load(e0 + j);
       if (aff_is_inf(Q)) continue;
       if constexpr (F::LAZY && B3 == 3) acc = proj_add_mixed_nr<F>(acc, Q);
       else acc = proj_add_mixed<F, B3>(acc, Q);
     }
-    if constexpr (F::LAZY && B3 == 3) acc = proj_canon(acc);
   }
+  // join the halves: complete addition with the partner lane's sum (neutral element where a half is empty)
+  Proj<F> other;
+#pragma unroll
+  for (int i = 0; i < F::N; i++) {
+    other.X.v[i] = __shfl_xor_sync(0xffffffffu, acc.X.v[i], 1);
+    other.Y.v[i] = __shfl_xor_sync(0xffffffffu, acc.Y.v[i], 1);
+    other.Z.v[i] = __shfl_xor_sync(0xffffffffu, acc.Z.v[i], 1);
+  }
+  if constexpr (F::LAZY && B3 == 3) acc = proj_canon(proj_add_nr<F>(acc, other));
+  else acc = proj_add<F, B3>(acc, other);
+  if (!live || half) return;
   uint4* o = buckets + (size_t)b * (3 * F::N / 4);
   st_aos<F>(o, acc.X);
   st_aos<F>(o + F::N / 4, acc.Y);
