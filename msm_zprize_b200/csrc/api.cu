@@ -220,7 +220,7 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->bases, &ctx->raw_points, &ctx->raw_scalars, &ctx->hs, &ctx->cnt, &ctx->cursor, &ctx->po,
+  DevBuf* all[] = {&ctx->bases, &ctx->raw_points, &ctx->raw_scalars, &ctx->hs, &ctx->cnt, &ctx->cntk, &ctx->cursor, &ctx->po,
                    &ctx->totals, &ctx->ent, &ctx->pairkey[0], &ctx->pairkey[1], &ctx->elem[0], &ctx->elem[1],
                    &ctx->prefix, &ctx->red[0], &ctx->red[1], &ctx->partial, &ctx->result, &ctx->buckets, &ctx->rp_tables, &ctx->fin, &ctx->others, &ctx->tilesum};
   for (DevBuf* b : all) release(*b);

@@ -71,7 +71,7 @@ struct msm_b200_ctx {
                                      // with 6 record sets + the workspace of the rounds exceed 180 GB
   int table_window = 0;              // MSM_B200_TABLE_WINDOW: forces the tables' window size (tuning)
   // workspace
-  DevBuf raw_points, raw_scalars, hs, cnt, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
+  DevBuf raw_points, raw_scalars, hs, cnt, cntk, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
   DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others, tilesum;
   unsigned long long* h_totals = nullptr;  // pinned
   uint32_t* h_result = nullptr;            // pinned
@@ -442,6 +442,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.pairkey = nullptr;
   sa.digits = nullptr;
   sa.bucket_stride = shared ? 0u : L;
+  sa.cnt_stride = sa.bucket_stride;
   sa.ent_stride = shared ? (uint32_t)ctx->n_bases : 0u;
   LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
   int e1 = T.mark();
@@ -563,29 +564,38 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
 
   int e0 = T.mark();
   // --- GLV + digits + histogram
+  // shared buckets with few buckets: count per (window, bucket) and merge (see SortArgs::cnt)
+  const bool split_counts = shared && L <= (1u << 16);
+  const size_t NBK = (shared && !split_counts) ? (size_t)L : (size_t)K * L;  // counters the two sort passes touch
   RET_IF(ensure(ctx, ctx->hs, S * 16));
   RET_IF(ensure(ctx, ctx->cnt, NB * 4));
-  RET_IF(ensure(ctx, ctx->cursor, NB * 4));
+  RET_IF(ensure(ctx, ctx->cursor, NBK * 4));
+  if (split_counts) RET_IF(ensure(ctx, ctx->cntk, NBK * 4));
   RET_IF(ensure(ctx, ctx->po, (size_t)(MAX_ROUNDS + 1) * NB * 4));
   RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
   LAUNCH(ctx, k_glv<G>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
-  CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
-  CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
+  uint32_t* cnt_hist = split_counts ? (uint32_t*)ctx->cntk.p : (uint32_t*)ctx->cnt.p;
+  CK(cudaMemsetAsync(cnt_hist, 0, NBK * 4, ctx->stream));
+  if (!split_counts) CK(cudaMemsetAsync(ctx->cursor.p, 0, NBK * 4, ctx->stream));
   SortArgs sa;
   sa.hs = (const uint4*)ctx->hs.p;
   sa.S = S;
   sa.c = c;
   sa.K = K;
   sa.L = L;
-  sa.cnt = (uint32_t*)ctx->cnt.p;
+  sa.cnt = cnt_hist;
   sa.cursor = (uint32_t*)ctx->cursor.p;
   sa.po0 = (const uint32_t*)ctx->po.p;
   sa.ent = nullptr;
   sa.pairkey = nullptr;
   sa.digits = digits_dump_dev;
   sa.bucket_stride = shared ? 0u : L;
+  sa.cnt_stride = (shared && !split_counts) ? 0u : L;
   sa.ent_stride = shared ? (uint32_t)(2 * ctx->n_bases) : 0u;
   LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
+  if (split_counts)
+    LAUNCH(ctx, k_merge_counts, cdiv(L, 256), 256, (const uint32_t*)ctx->cntk.p, K, L, (uint32_t*)ctx->cnt.p,
+           (uint32_t*)ctx->cursor.p);
   int e1 = T.mark();
   // --- offsets for every round; the host needs the totals (one sync), the scatter does not: it is queued
   //     first, sized by the upper bound 2 * P0 <= S * K + NB, so the GPU keeps working while the host wakes up

@@ -153,8 +153,13 @@ struct SortArgs {
   size_t S;
   int c, K;
   uint32_t L;
-  uint32_t* cnt;     // K*L bucket counts
-  uint32_t* cursor;  // K*L running positions (scatter)
+  uint32_t* cnt;     // counts, indexed k * cnt_stride + bucket.  Classic: cnt_stride = L.  Shared buckets with few
+                     //   buckets (L <= 2^16): still one counter per (window, bucket), merged into the L shared counts
+                     //   afterwards (k_merge_counts) -- K times fewer atomics per address; with many buckets the
+                     //   windows count straight into the shared array (cnt_stride = 0: K times fewer addresses)
+  uint32_t* cursor;  // running positions (scatter), same indexing; start at 0, or (merged counts) at the window's
+                     //   offset inside the shared bucket
+  uint32_t cnt_stride;
   const uint32_t* po0;  // pair offsets of round 0
   uint32_t* ent;        // sorted entries, 2 * P0 slots
   uint32_t* pairkey;    // bucket of every round-0 pair
@@ -178,15 +183,31 @@ __global__ void k_hist_scatter(SortArgs a) {
     uint32_t l = signed_digit<4>(s, k, a.c, carry);
     if (a.digits && !SCATTER) a.digits[h * a.K + k] = l | ((l ? (carry ^ sign) : 0u) << 31);
     if (l == 0) continue;
-    uint32_t b = (uint32_t)k * a.bucket_stride + (l - 1);
+    const uint32_t kb = (uint32_t)k * a.cnt_stride + (l - 1);
     if (!SCATTER) {
-      atomicAdd(&a.cnt[b], 1u);
+      atomicAdd(&a.cnt[kb], 1u);
     } else {
-      uint32_t pos = atomicAdd(&a.cursor[b], 1u);
+      const uint32_t b = (uint32_t)k * a.bucket_stride + (l - 1);
+      uint32_t pos = atomicAdd(&a.cursor[kb], 1u);
       uint32_t slot = 2u * a.po0[b] + pos;
       a.ent[slot] = ((uint32_t)h + (uint32_t)k * a.ent_stride) | ((carry ^ sign) << 31);  // (pairkey: k_fill_pairkey)
     }
   }
+}
+
+// Shared buckets: cnt[b] = sum over the windows of cntk[k * L + b], and cursor[k * L + b] = where window k's
+// entries start inside bucket b.
+static __global__ void __launch_bounds__(256) k_merge_counts(const uint32_t* __restrict__ cntk, int K, uint32_t L,
+                                                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ cursor) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= L) return;
+  uint32_t run = 0;
+  for (int k = 0; k < K; k++) {
+    const uint32_t c = cntk[(size_t)k * L + b];
+    cursor[(size_t)k * L + b] = run;
+    run += c;
+  }
+  cnt[b] = run;
 }
 
 // Exclusive scan over buckets of the pair slots, for every tree round r at once (grid.y = round):

@@ -347,3 +347,23 @@ def test_entry_count_limit_is_an_error_not_an_overflow(mz):
         assert e.value.code == -1  # MSM_E_INVALID
         r = eng.run(d_sc, 1 << 10, on_device=True)             # the context stays usable
         assert not r.is_zero
+
+
+def test_python_binding_refuses_short_buffers(mz):
+    """A host buffer shorter than n * item bytes must be refused with MSM_E_INVALID before the copy could read
+    past its end (the N-API addon bounds-checks its regions the same way)."""
+    from msm_zprize_b200 import _lib as L
+    with mz.MsmEngine("bls12-377") as eng:
+        with pytest.raises(mz.MsmError) as e:
+            eng.set_bases(bytes(96 * 3), 4)
+        assert e.value.code == L.E_INVALID
+        eng.set_bases(bytes(96 * 4), 4)
+        with pytest.raises(mz.MsmError):
+            eng.run(bytes(32 * 3), 4)
+        with pytest.raises(mz.MsmError):
+            eng.msm(bytes(32 * 4), bytes(96 * 3), 4)
+        with pytest.raises(mz.MsmError):
+            eng.set_bases(np.zeros(10, dtype=np.uint32), 4, mz.LAYOUT_LIMB29_MONT)
+    buf = mz.PinnedBuffer(64)
+    buf.free()
+    assert buf.array is None

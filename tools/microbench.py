@@ -7,8 +7,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msm_zprize_b200.engine import microbench  # noqa: E402
 
-# (variants 0 / 1 of the library are not reported: ptxas rewrites their chains into mixed sequences)
-NAMES = {2: "imad_wide_carry", 5: "imad_hi", 8: "iadd", 3: "modmul_12limb", 4: "modmul_8limb",
+# SASS of every variant: profiles/r02_sass_hist_mb_imad_*.txt (0: pure IMAD; 1: ptxas splits every mad.wide.u32 with a
+# 64-bit addend into IMAD.WIDE.U32 + IADD3 pairs, so its rate is the rate of that pair, not of IMAD.WIDE alone;
+# 2: IMAD.WIDE.U32(.X) carry chains, the form the Montgomery product uses -- the roofline denominator)
+NAMES = {0: "imad_lo", 1: "imad_wide_plus_iadd3", 2: "imad_wide_carry", 5: "imad_hi", 8: "iadd", 3: "modmul_12limb", 4: "modmul_8limb",
          6: "modsqr_12limb", 7: "modsqr_8limb", 9: "dbl_chain_quad_12limb", 10: "dbl_chain_lone_12limb",
          11: "dbl_chain_quad_8limb"}
 out = {}
