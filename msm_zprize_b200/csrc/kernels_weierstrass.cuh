@@ -630,7 +630,9 @@ __global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_bwd(RoundArg
     uint32_t b, j;
     Fe<F> pre = ld_soa<F>(a.prefix, a.P, i);  // (unused garbage for pass-through pairs)
     load_pair<F, R0>(a, i, A, B, b, j);
-    const uint32_t pon = a.po_n[b];
+    // round 0 (gathered operands: the tightest register budget) looks the output slot up after the arithmetic
+    // instead of keeping it live across it (it was the 20 bytes that spilled at 128 registers)
+    uint32_t pon = R0 ? 0u : a.po_n[b];
     Fe<F> d;
     int cs = aff_add_prepare(A, B, d);
     Fe<F> id = inv;
@@ -643,6 +645,10 @@ __global__ void __launch_bounds__(ACC_THREADS, acc_resident<F>()) k_bwd(RoundArg
     if (n <= 2) {  // one element left after this round: the bucket sum
       a.fin.store(b, R);
     } else {
+      if (R0) {
+        pon = a.po_n[b];
+        j = (uint32_t)i - a.po_r[b];
+      }
       size_t e = 2 * (size_t)pon + j;
       a.out.store(e, R);
       if (!(e & 1)) a.pairkey_next[e >> 1] = b;

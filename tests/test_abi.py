@@ -49,9 +49,11 @@ def test_no_silent_cpu_fallback_without_gpu(lib):
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    from msm_zprize_b200 import MsmEngine, MsmError
+    from msm_zprize_b200 import MsmEngine, MsmError, MultiMsmEngine
     with pytest.raises(MsmError):
         MsmEngine("bls12-377", device=0)
+    with pytest.raises(MsmError):
+        MultiMsmEngine("bls12-377", [0, 1])
 
 
 def test_product_does_not_import_the_oracle():
