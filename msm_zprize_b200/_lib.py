@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmsm_b200.so")
+# (MSM_B200_LIB: development override, e.g. a build with other compile-time constants under build/)
+LIB_PATH = os.environ.get("MSM_B200_LIB") or os.path.join(_HERE, "csrc", "libmsm_b200.so")
 
 # enums (include/msm_b200.h)
 CURVE_BLS12_377_G1, CURVE_PALLAS, CURVE_ED_ON_BLS12_377, CURVE_BLS12_381_G1 = 0, 1, 2, 3
