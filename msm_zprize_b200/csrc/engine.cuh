@@ -363,7 +363,8 @@ static int reduce_buckets(msm_b200_ctx* ctx, const Loader& ld, size_t NB, int K,
   // level 0: 8 buckets per thread (measured best of 4 / 8 / 16 / 32 at 2^18 buckets: 1.59 / 1.28 / 1.44 / 1.94 ms
   // for the whole reduction); few buckets: 4 per lane quad
   const bool few = NB <= ((size_t)1 << 16);
-  const int gb0 = ctx->reduce_gb0 > 0 ? ctx->reduce_gb0 : (few ? 2 : 3);
+  // (2^21 shared buckets, c = 22: 16 per thread -- 3.59 -> 3.10 ms; 32 per thread 2.91 ms but a longer serial tail)
+  const int gb0 = ctx->reduce_gb0 > 0 ? ctx->reduce_gb0 : (few ? 2 : (NB >= ((size_t)1 << 20) ? 4 : 3));
   const size_t warp_min = ctx->reduce_warp_min > 0 ? ctx->reduce_warp_min : (few ? (size_t)1 << 16 : (size_t)4096);
   const bool quad0 = ctx->reduce_quad0 >= 0 ? ctx->reduce_quad0 != 0 : few;
   int gb = remaining < gb0 ? remaining : gb0;
