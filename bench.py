@@ -376,9 +376,10 @@ def check_combined_point(g, sh, curve, s):
     return (res.x, res.y) == acc
 
 
-def strong_case(g, curve, T, steps, peak_lp):
+def strong_case(g, curve, T, steps, peak_lp, cpu=False):
     """Fixed total of 2^T points range-sharded over the ranks (BASELINE.json configs 4 / 5), and the same
-    problem on ONE GPU (rank 0, the others wait) for the strong-scaling efficiency."""
+    problem on ONE GPU (rank 0, the others wait) for the strong-scaling efficiency.  `cpu`: also time the CPU
+    port on the same inputs (N = 1 only, sizes the reference itself can run) and compare the points."""
     lw = int(math.log2(g.world))
     te = curve == "ed-on-bls12-377"
     out = {"curve": curve, "total_log2n": T, "n_gpus": g.world, "points_per_gpu": 1 << (T - lw)}
@@ -390,6 +391,18 @@ def strong_case(g, curve, T, steps, peak_lp):
                 "shared_buckets": tm["shared_buckets"],
                 "whole_msm_frac_per_gpu": w_alg(curve, 1 << (T - lw), tm["window_bits"], te, bool(tm["shared_buckets"])) /
                 (med * 1e-3) / peak_lp if peak_lp else None})
+    if cpu and g.world == 1:
+        from oracle.port import Port  # baseline / checker only
+        n, nb, threads = 1 << T, CURVES[curve][0], os.cpu_count() or 1
+        port = Port(curve)
+        prepared = port.prepare_points(sh.pts.cpu().numpy().tobytes(), n, threads)
+        s_last = (2 + steps - 1) % sh.scal.shape[0]  # the scalars of the last timed step
+        times, res_cpu = cpu_time_msm(port, sh.scal[s_last].cpu().numpy().tobytes(), prepared, n, threads,
+                                      port.default_window(n), 2)
+        out["cpu_port_ms"] = min(times) * 1e3
+        out["cpu_port_window_bits"] = port.default_window(n)
+        out["cpu_port_cores"] = threads
+        out["same_point_as_cpu_port"] = (res.x, res.y, res.is_zero) == res_cpu
     sh.close()
     if g.world > 1:
         single = None
@@ -509,9 +522,10 @@ def main():
     strong = None
     if not args.no_strong and curve == "bls12-377" and not args.total_log2n and args.log2n == 18:
         strong = []
-        for cv, T in (("bls12-377", 22), ("bls12-377", 26), ("ed-on-bls12-377", 22)):
+        # config 5: BLS12-377 sweep 2^20 .. 2^26; config 4: ed-on-bls12-377 2^22
+        for cv, T in (("bls12-377", 20), ("bls12-377", 22), ("bls12-377", 24), ("bls12-377", 26), ("ed-on-bls12-377", 22)):
             try:
-                strong.append(strong_case(g, cv, T, args.strong_steps, peak_lp))
+                strong.append(strong_case(g, cv, T, args.strong_steps, peak_lp, cpu=(T == 20)))
             except Exception as e:  # a failed extra must not take the headline line with it
                 strong.append({"curve": cv, "total_log2n": T, "error": repr(e)[:300]})
                 barrier(g)
@@ -611,6 +625,9 @@ def main():
     }
     if strong is not None:
         out["strong"] = strong
+        if any(c.get("same_point_as_cpu_port") is False for c in strong):
+            out["ok"] = ok = False
+            out["notes"].append("a strong-block GPU result differs from the CPU port")
     emit(out)
     if dist is not None:
         dist.destroy_process_group()
