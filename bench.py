@@ -327,7 +327,8 @@ class Sharded:
         if not solo:
             barrier(g)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        acc = {"hot_kernel_ms": 0.0, "hot_kernel_launches": 0, "kernel_launches": 0, "n_adds": 0}
+        acc = {"hot_kernel_ms": 0.0, "hot_kernel_launches": 0, "kernel_launches": 0, "n_adds": 0, "fwd_round0_ms": 0.0,
+               "fwd_round0_pairs": 0}
         last_tm = last_res = None
         for i in range(steps):
             g.flush.fill_(i & 0xFF)
@@ -568,6 +569,31 @@ def main():
         "share_of_step": hot_ms / (sum(ms_steps)) if world == 1 else None,
         "whole_msm_frac": (w_alg(curve, n, c_used, te, shared) / (ms_per_step * 1e-3)) / peak_lp if peak_lp else None,
     }
+
+    # secondary roofline: the round-0 forward pass, the HBM-bound kernel of the path (random gathers of the x
+    # coordinates out of the resident record sets), against the measured copy bandwidth of MEASURED_PEAKS.json
+    if not te and acc["fwd_round0_ms"] > 0:
+        try:
+            hbm_peak, hbm_src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json (measured copy)"
+        except (OSError, KeyError, ValueError):
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+        fb = 4 * n32
+        bytes_pair = 2 * fb + fb + 8 + 4 + 8  # two x coordinates in, one prefix product out, entries, pair key, offsets
+        fwd_gbs = acc["fwd_round0_pairs"] * bytes_pair / (acc["fwd_round0_ms"] * 1e-3) / 1e9
+        ncu_bytes = None
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+            if rec["workload"] == workload_name(curve, args.log2n) and args.window == 0:
+                ncu_bytes = rec["k_fwd_per_launch"][0]["dram_bytes"]
+        except (OSError, KeyError, ValueError, IndexError):
+            pass
+        roofline["secondary"] = {
+            "bound": "hbm", "kernel": "k_fwd round 0 (forward prefix products over gathered base points)",
+            "achieved": fwd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_gbs / hbm_peak,
+            "avg_launch_ms": acc["fwd_round0_ms"] / steps, "algorithmic_bytes": acc["fwd_round0_pairs"] / steps * bytes_pair,
+            "traffic": ncu_bytes, "peak_source": hbm_src,
+            "note": "48-byte gathers out of 96-byte records move whole 64-byte lines: the ncu capture shows about 2.2x the "
+                    "algorithmic bytes, i.e. the DRAM side runs at about twice the fraction quoted here"}
 
     # ---- CPU baseline on the SAME workload (rank 0, N = 1 only): the port on all host cores, and the parity
     #      check of the GPU result at full size

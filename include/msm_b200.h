@@ -80,6 +80,8 @@ typedef struct msm_b200_timing {
   int rounds;               /* batched-affine tree rounds */
   unsigned long long n_adds;/* point additions finished inside the dominant kernel's launches */
   int shared_buckets;       /* 1: resident window tables 2^(kc) G were used, all windows share one bucket set */
+  float fwd_round0_ms;      /* batched-affine path: the round-0 forward pass (random gathers of base points, HBM-bound) */
+  unsigned fwd_round0_pairs;/*   and the point pairs it went through */
   int reserved;
 } msm_b200_timing;
 

@@ -27,7 +27,7 @@ class Timing(C.Structure):
         ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("hot_kernel_ms", C.c_float),
         ("hot_kernel_launches", C.c_int), ("kernel_launches", C.c_int), ("window_bits", C.c_int),
         ("n_windows", C.c_int), ("rounds", C.c_int), ("n_adds", C.c_ulonglong),
-        ("shared_buckets", C.c_int), ("reserved", C.c_int),
+        ("shared_buckets", C.c_int), ("fwd_round0_ms", C.c_float), ("fwd_round0_pairs", C.c_uint), ("reserved", C.c_int),
     ]
 
     def as_dict(self):

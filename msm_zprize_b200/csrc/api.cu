@@ -95,6 +95,7 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
   }
   int rc;
   ctx->pending.valid = false;
+  ctx->pending.fwd0[0] = ctx->pending.fwd0[1] = -1;
   ctx->pending.window_bits = c;
   ctx->pending.n_windows = 0;
   ctx->pending.shared_buckets = 0;

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -33,6 +34,8 @@ struct PendingTiming {
   int window_bits = 0, n_windows = 0, rounds = 0, shared_buckets = 0;
   unsigned long long n_adds = 0;
   int h2d[2] = {-1, -1};  // scalar upload, set by the entry point
+  int fwd0[2] = {-1, -1}; // round-0 forward pass (k_fwd over the gathered base points)
+  unsigned long long fwd0_pairs = 0;
 };
 
 struct msm_b200_ctx {
@@ -195,6 +198,10 @@ static int resolve_timing(msm_b200_ctx* ctx, msm_b200_timing* tm) {
   tm->rounds = pt.rounds;
   tm->n_adds = pt.n_adds;
   if (pt.h2d[0] >= 0) tm->h2d_ms = T.ms(pt.h2d[0], pt.h2d[1]);
+  if (pt.fwd0[0] >= 0) {
+    tm->fwd_round0_ms = T.ms(pt.fwd0[0], pt.fwd0[1]);
+    tm->fwd_round0_pairs = (unsigned)std::min<unsigned long long>(pt.fwd0_pairs, 0xFFFFFFFFull);
+  }
   tm->kernel_launches = ctx->launches;
   return 0;
 }
@@ -545,6 +552,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   constexpr size_t FE = F::N * 4;
   Timer T(ctx);
   ctx->pending.valid = false;
+  ctx->pending.fwd0[0] = ctx->pending.fwd0[1] = -1;
   const int b = G::MAXBITS;  // Scalar.maxBits, src/wasm/glv.ts:216-226
   const int K = (b + 1 + c - 1) / c;
   ctx->pending.window_bits = c;
@@ -741,9 +749,13 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
       Mtree = M1;
     }
     a.invtot = nullptr;  // set after invert_totals (which may grow its buffers)
-    if (r == 0) {
+    if (r == 0) {  // the round-0 forward pass is the HBM-bound kernel of the path (random gathers): timed on its own
+      int f0 = T.mark();
       if (blk) LAUNCH(ctx, (k_fwd<F, true, true>), grid, ACC_THREADS, a);
       else LAUNCH(ctx, (k_fwd<F, true, false>), grid, ACC_THREADS, a);
+      int f1 = T.mark();
+      ctx->pending.fwd0[0] = f0, ctx->pending.fwd0[1] = f1;
+      ctx->pending.fwd0_pairs = P;
     } else {
       if (blk) LAUNCH(ctx, (k_fwd<F, false, true>), grid, ACC_THREADS, a);
       else LAUNCH(ctx, (k_fwd<F, false, false>), grid, ACC_THREADS, a);

@@ -41,8 +41,8 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_header(lib):
     from msm_zprize_b200 import _lib
     assert ctypes.sizeof(_lib.Point) == 100
-    # 9 floats + 5 ints + 8-byte counter + 2 ints, 8-byte aligned
-    assert ctypes.sizeof(_lib.Timing) == 72
+    # 9 floats + 5 ints + 8-byte counter + int, float, unsigned, int: 8-byte aligned
+    assert ctypes.sizeof(_lib.Timing) == 80
 
 
 def test_no_silent_cpu_fallback_without_gpu(lib):
