@@ -197,6 +197,9 @@ const char* msm_b200_multi_last_error(const msm_b200_multi* m);
 int msm_b200_multi_devices(const msm_b200_multi* m);
 /* "ncclAllGather (NCCL <version>, ncclCommInitAll)" | "peer copies (cudaMemcpyPeerAsync)" | "none (single device)" */
 const char* msm_b200_multi_gather_kind(const msm_b200_multi* m);
+/* the range of a set of n points that device i of n_dev owns: [first, first + count), ceil(n / n_dev) points each
+ * like range() (src/threads/threads.ts:354-359); pure host arithmetic, needs no GPU */
+void msm_b200_multi_shard_range(size_t n, int i, int n_dev, size_t* first, size_t* count);
 /* the per-device context i (generators, device memory helpers); owned by `m` */
 msm_b200_ctx* msm_b200_multi_ctx(msm_b200_multi* m, int i);
 /* msm_b200_set_bases over all devices: host points, range-sharded by the library */

@@ -55,7 +55,7 @@ EXPORTS = [
     "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
     "msm_b200_host_free_pinned", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
     "msm_b200_multi_create", "msm_b200_multi_destroy", "msm_b200_multi_last_error", "msm_b200_multi_devices",
-    "msm_b200_multi_gather_kind", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_set_bases_sharded",
+    "msm_b200_multi_gather_kind", "msm_b200_multi_shard_range", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_set_bases_sharded",
     "msm_b200_multi_run", "msm_b200_multi_run_sharded", "msm_b200_multi_msm", "msm_b200_multi_last_timings",
 ]
 # include/msm_b200_test.h
@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     L.msm_b200_multi_devices.argtypes = [vp]
     L.msm_b200_multi_gather_kind.argtypes = [vp]
     L.msm_b200_multi_gather_kind.restype = C.c_char_p
+    L.msm_b200_multi_shard_range.argtypes = [sz, ci, ci, C.POINTER(sz), C.POINTER(sz)]
+    L.msm_b200_multi_shard_range.restype = None
     L.msm_b200_multi_ctx.argtypes = [vp, ci]
     L.msm_b200_multi_ctx.restype = vp
     L.msm_b200_multi_set_bases.argtypes = [vp, vp, sz, ci]

@@ -283,6 +283,13 @@ void msm_b200_multi_destroy(msm_b200_multi* m) {
   delete m;
 }
 
+void msm_b200_multi_shard_range(size_t n, int i, int n_dev, size_t* first, size_t* count) {
+  size_t lo = 0, cnt = 0;
+  if (n_dev > 0 && i >= 0 && i < n_dev) shard_range(n, i, n_dev, lo, cnt);
+  if (first) *first = lo;
+  if (count) *count = cnt;
+}
+
 const char* msm_b200_multi_last_error(const msm_b200_multi* m) { return m ? m->err.c_str() : g_err.c_str(); }
 int msm_b200_multi_devices(const msm_b200_multi* m) { return m ? m->n_dev : 0; }
 const char* msm_b200_multi_gather_kind(const msm_b200_multi* m) { return m ? m->gather_kind.c_str() : ""; }

@@ -49,6 +49,21 @@ def test_shard_range_covers_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
 
 
+def test_library_shard_range_equals_the_harness():
+    """msm_b200_multi_* (one process, all GPUs) and the torchrun harness must cut a point set the same way."""
+    import ctypes as C
+    from msm_zprize_b200 import _lib
+    from msm_zprize_b200.dist import shard_range
+    L = _lib.lib()
+    for n in (0, 1, 7, 8, 1000, (1 << 18) + 3, 1 << 26):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                lo, cnt = C.c_size_t(), C.c_size_t()
+                L.msm_b200_multi_shard_range(n, r, world, C.byref(lo), C.byref(cnt))
+                a, b = shard_range(n, r, world)
+                assert (lo.value, lo.value + cnt.value) == (a, b), (n, world, r)
+
+
 def test_two_rank_sharded_msm_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
