@@ -81,15 +81,36 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
   if (window_bits <= 0 && ctx->table_c > 0 && n >= ((size_t)1 << 12) && (te || form == MSM_FORM_AFFINE_GLV)) c = ctx->table_c;
   if (c < 1 || c > 24) return fail(ctx, MSM_E_INVALID, "window_bits out of range [1,24]");
   Timer T(ctx);
-  int t0 = T.mark();
+  int t0 = -1, t1 = -1;
   const void* d_s = scalars;
+  ctx->sc_chunks = 0;
   if (!on_device && n) {
-    size_t bytes = n * scalar_bytes(layout);
+    const size_t sb = scalar_bytes(layout), bytes = n * sb;
     RET_IF(ensure(ctx, ctx->raw_scalars, bytes));
-    CK(cudaMemcpyAsync(ctx->raw_scalars.p, scalars, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n >= ((size_t)1 << 16) && !ctx->bases_pending) {
+      // resident bases: the scalars go up in pieces on the copy stream and the per-scalar phases follow piece by
+      // piece (run_*); the copy stream first waits for whatever still reads the buffer on the main stream.
+      // (One-shot call: the copy stream is busy with the points, the scalars stay on the main stream.)
+      CK(cudaEventRecord(ctx->sc_start, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->sc_start, 0));
+      t0 = T.mark(ctx->copy_stream);
+      for (int j = 0; j < msm_b200_ctx::SC_CHUNKS; j++) {
+        size_t lo, hi;
+        scalar_piece(n, msm_b200_ctx::SC_CHUNKS, j, lo, hi);
+        if (hi > lo)
+          CK(cudaMemcpyAsync((char*)ctx->raw_scalars.p + lo * sb, (const char*)scalars + lo * sb, (hi - lo) * sb,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->sc_ready[j], ctx->copy_stream));
+      }
+      t1 = T.mark(ctx->copy_stream);
+      ctx->sc_chunks = msm_b200_ctx::SC_CHUNKS;
+    } else {
+      t0 = T.mark();
+      CK(cudaMemcpyAsync(ctx->raw_scalars.p, scalars, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      t1 = T.mark();
+    }
     d_s = ctx->raw_scalars.p;
   }
-  int t1 = T.mark();
   if (tm) {
     memset(tm, 0, sizeof *tm);
   }
@@ -103,12 +124,16 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
     rc = ops_of(ctx->curve)->zero_partial(ctx);
   else
     rc = ops_of(ctx->curve)->run(ctx, d_s, n, layout, form, c, tm, digits_dump_dev);
+  if (ctx->sc_chunks > 0) {  // an error path left the pieces unconsumed: the main stream must still order behind them
+    for (int j = 0; j < ctx->sc_chunks; j++) cudaStreamWaitEvent(ctx->stream, ctx->sc_ready[j], 0);
+    ctx->sc_chunks = 0;
+  }
   RET_IF(rc);
   RET_IF(wait_for_bases(ctx));  // (no-op unless the MSM never touched the bases, e.g. all-zero scalars)
   ctx->pending.h2d[0] = t0;
   ctx->pending.h2d[1] = t1;
   if (tm) {
-    if (ctx->pending.valid) tm->h2d_ms = T.ms(t0, t1);
+    if (ctx->pending.valid && t0 >= 0) tm->h2d_ms = T.ms(t0, t1);
     tm->kernel_launches = ctx->launches;
   }
   return 0;
@@ -203,7 +228,12 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->bases_ready, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->totals_ready, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->totals_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sc_start, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sc_ready[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sc_ready[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sc_ready[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->sc_ready[3], cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, MSM_E_CUDA, "stream / event creation failed");
   }
@@ -235,6 +265,9 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->bases_ready) cudaEventDestroy(ctx->bases_ready);
   if (ctx->totals_ready) cudaEventDestroy(ctx->totals_ready);
+  if (ctx->sc_start) cudaEventDestroy(ctx->sc_start);
+  for (cudaEvent_t e : ctx->sc_ready)
+    if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

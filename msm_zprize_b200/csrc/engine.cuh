@@ -48,6 +48,12 @@ struct msm_b200_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t bases_ready = nullptr;
   cudaEvent_t totals_ready = nullptr;  // bucket totals have reached the pinned host buffer
+  // host scalars arrive in SC_CHUNKS pieces on the copy stream; the per-scalar phases (GLV / unpacking, digit
+  // histogram) run piece by piece behind them, so all but the last piece of the upload is hidden
+  static constexpr int SC_CHUNKS = 4;
+  cudaEvent_t sc_ready[SC_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t sc_start = nullptr;
+  int sc_chunks = 0;  // > 0: the current run's scalars come in that many pieces (consumed by the run)
   bool bases_pending = false;
   std::string err;
   int launches = 0;
@@ -147,6 +153,19 @@ static int wait_for_bases(msm_b200_ctx* ctx) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->bases_ready, 0));
     ctx->bases_pending = false;
   }
+  return 0;
+}
+
+// piece j of n scalars cut into `pieces` (multiples of 256 scalars, the last takes the rest)
+static void scalar_piece(size_t n, int pieces, int j, size_t& lo, size_t& hi) {
+  size_t per = ((n + pieces - 1) / pieces + 255) & ~(size_t)255;
+  lo = std::min(n, per * (size_t)j);
+  hi = (j == pieces - 1) ? n : std::min(n, lo + per);
+}
+
+// before the per-scalar kernels of piece j: wait for its upload (no-op for scalars that are already resident)
+static int wait_for_scalars(msm_b200_ctx* ctx, int j) {
+  if (ctx->sc_chunks > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->sc_ready[j], 0));
   return 0;
 }
 
@@ -434,7 +453,6 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   RET_IF(ensure(ctx, ctx->cursor, NB * 4));
   RET_IF(ensure(ctx, ctx->po, 2 * NB * 4));
   RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
-  LAUNCH(ctx, k_load_scalars<S>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   CK(cudaMemsetAsync(ctx->cnt.p, 0, NB * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->cursor.p, 0, NB * 4, ctx->stream));
   SortArgs sa;
@@ -452,7 +470,23 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   sa.bucket_stride = shared ? 0u : L;
   sa.cnt_stride = sa.bucket_stride;
   sa.ent_stride = shared ? (uint32_t)ctx->n_bases : 0u;
-  LAUNCH(ctx, k_hist_scatter8<false>, cdiv(n, 256), 256, sa);
+  {  // unpack + count, piece by piece behind the scalar upload
+    const int pieces = ctx->sc_chunks > 0 ? ctx->sc_chunks : 1;
+    const size_t sb = scalar_bytes(layout);
+    for (int j = 0; j < pieces; j++) {
+      size_t lo, hi;
+      scalar_piece(n, pieces, j, lo, hi);
+      RET_IF(wait_for_scalars(ctx, j));
+      if (hi <= lo) continue;
+      LAUNCH(ctx, k_load_scalars<S>, cdiv(hi - lo, 128), 128, (const uint8_t*)d_scalars + lo * sb, hi - lo, layout,
+             (uint4*)ctx->hs.p + 2 * lo);
+      SortArgs sp = sa;
+      sp.hs = sa.hs + 2 * lo;
+      sp.S = hi - lo;
+      LAUNCH(ctx, k_hist_scatter8<false>, cdiv(hi - lo, 256), 256, sp);
+    }
+    ctx->sc_chunks = 0;
+  }
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
   RET_IF(launch_scan(ctx, NB, 2, BUCKET_SPLIT));  // po[0]: padded entry offsets, po[1]: virtual-bucket offsets
@@ -582,7 +616,6 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   if (split_counts) RET_IF(ensure(ctx, ctx->cntk, NBK * 4));
   RET_IF(ensure(ctx, ctx->po, (size_t)(MAX_ROUNDS + 1) * NB * 4));
   RET_IF(ensure(ctx, ctx->totals, N_TOTALS * 8));
-  LAUNCH(ctx, k_glv<G>, cdiv(n, 128), 128, (const uint8_t*)d_scalars, n, layout, (uint4*)ctx->hs.p);
   uint32_t* cnt_hist = split_counts ? (uint32_t*)ctx->cntk.p : (uint32_t*)ctx->cnt.p;
   CK(cudaMemsetAsync(cnt_hist, 0, NBK * 4, ctx->stream));
   if (!split_counts) CK(cudaMemsetAsync(ctx->cursor.p, 0, NBK * 4, ctx->stream));
@@ -601,7 +634,25 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
   sa.bucket_stride = shared ? 0u : L;
   sa.cnt_stride = (shared && !split_counts) ? 0u : L;
   sa.ent_stride = shared ? (uint32_t)(2 * ctx->n_bases) : 0u;
-  LAUNCH(ctx, k_hist_scatter<false>, cdiv(S, 256), 256, sa);
+  {  // decompose + count, piece by piece behind the scalar upload (the digit dump of the tests: one piece)
+    const int pieces = (ctx->sc_chunks > 0 && !digits_dump_dev) ? ctx->sc_chunks : 1;
+    const size_t sb = scalar_bytes(layout);
+    for (int j = 0; j < pieces; j++) {
+      size_t lo, hi;
+      scalar_piece(n, pieces, j, lo, hi);
+      if (ctx->sc_chunks > 0) {
+        if (pieces > 1) RET_IF(wait_for_scalars(ctx, j));
+        else for (int u = 0; u < ctx->sc_chunks; u++) RET_IF(wait_for_scalars(ctx, u));
+      }
+      if (hi <= lo) continue;
+      LAUNCH(ctx, k_glv<G>, cdiv(hi - lo, 128), 128, (const uint8_t*)d_scalars + lo * sb, hi - lo, layout, (uint4*)ctx->hs.p + 2 * lo);
+      SortArgs sp = sa;
+      sp.hs = sa.hs + 2 * lo;
+      sp.S = 2 * (hi - lo);
+      LAUNCH(ctx, k_hist_scatter<false>, cdiv(2 * (hi - lo), 256), 256, sp);
+    }
+    ctx->sc_chunks = 0;
+  }
   if (split_counts)
     LAUNCH(ctx, k_merge_counts, cdiv(L, 256), 256, (const uint32_t*)ctx->cntk.p, K, L, (uint32_t*)ctx->cnt.p,
            (uint32_t*)ctx->cursor.p);
