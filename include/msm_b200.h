@@ -177,6 +177,11 @@ int msm_b200_dev_alloc(msm_b200_ctx* ctx, void** out_dev, size_t bytes);
 int msm_b200_dev_free(msm_b200_ctx* ctx, void* dev);
 int msm_b200_host_alloc_pinned(void** out_host, size_t bytes);
 int msm_b200_host_free_pinned(void* host);
+/* Page-locks memory the caller already owns (the buffer behind a WebAssembly.Memory): uploads from it then run as
+ * asynchronous DMA at PCIe speed instead of being staged through a bounce buffer.  Undo before the memory is freed
+ * or grown (a grown wasm memory has a new buffer). */
+int msm_b200_host_register(void* host, size_t bytes);
+int msm_b200_host_unregister(void* host);
 int msm_b200_memcpy_d2h(msm_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int msm_b200_memcpy_h2d(msm_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 

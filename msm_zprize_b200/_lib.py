@@ -53,7 +53,7 @@ EXPORTS = [
     "msm_b200_random_scalars", "msm_b200_point_bytes", "msm_b200_scalar_bytes",
     "msm_b200_random_points_at", "msm_b200_random_scalars_at",
     "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
-    "msm_b200_host_free_pinned", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
+    "msm_b200_host_free_pinned", "msm_b200_host_register", "msm_b200_host_unregister", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
     "msm_b200_multi_create", "msm_b200_multi_destroy", "msm_b200_multi_last_error", "msm_b200_multi_devices",
     "msm_b200_multi_gather_kind", "msm_b200_multi_shard_range", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_set_bases_sharded",
     "msm_b200_multi_run", "msm_b200_multi_run_sharded", "msm_b200_multi_msm", "msm_b200_multi_last_timings",
@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.msm_b200_dev_free.argtypes = [vp, vp]
     L.msm_b200_host_alloc_pinned.argtypes = [C.POINTER(vp), sz]
     L.msm_b200_host_free_pinned.argtypes = [vp]
+    L.msm_b200_host_register.argtypes = [vp, sz]
+    L.msm_b200_host_unregister.argtypes = [vp]
     L.msm_b200_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.msm_b200_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     L.msm_b200_multi_create.argtypes = [C.POINTER(vp), ci, C.POINTER(ci), ci]

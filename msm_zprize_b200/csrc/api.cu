@@ -393,6 +393,18 @@ int msm_b200_host_free_pinned(void* host) {
   CK(cudaFreeHost(host));
   return 0;
 }
+int msm_b200_host_register(void* host, size_t bytes) {
+  msm_b200_ctx* ctx = nullptr;
+  if (!host || !bytes) return fail(nullptr, MSM_E_INVALID, "bad arguments");
+  CK(cudaHostRegister(host, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int msm_b200_host_unregister(void* host) {
+  msm_b200_ctx* ctx = nullptr;
+  if (!host) return fail(nullptr, MSM_E_INVALID, "bad arguments");
+  CK(cudaHostUnregister(host));
+  return 0;
+}
 int msm_b200_memcpy_d2h(msm_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   if (!ctx) return fail(ctx, MSM_E_INVALID, "null context");
   CK(cudaSetDevice(ctx->device));

@@ -13,6 +13,9 @@
  *   run(ctx, memoryBytes, byteOffset, n, layout, form, windowBits)   -> Promise<{x, y, isZero, timing}>
  *       (memoryBytes: the Uint8Array over the wasm memory)
  *   destroy(ctx)
+ *   pinMemory(memoryBytes) / unpinMemory(memoryBytes)
+ *       page-lock the buffer behind a wasm memory (once, after the memory has its final size), so that uploads from
+ *       it are asynchronous DMA at PCIe speed; unpin before the memory grows or is dropped
  *
  * `setBases` and `run` do their work in napi async work (off the event loop): the reference's msm is async as
  * well (src/msm-batched-affine.ts:74-83) and the main thread must stay responsive
@@ -317,12 +320,33 @@ static napi_value start_job(napi_env env, napi_callback_info info, int is_run) {
 static napi_value SetBases(napi_env env, napi_callback_info info) { return start_job(env, info, 0); }
 static napi_value Run(napi_env env, napi_callback_info info) { return start_job(env, info, 1); }
 
+static napi_value pin_or_unpin(napi_env env, napi_callback_info info, int pin) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  napi_typedarray_type type;
+  size_t len = 0, off = 0;
+  void* data = NULL;
+  napi_value ab;
+  if (argc < 1 || napi_get_typedarray_info(env, argv[0], &type, &len, &data, &ab, &off) != napi_ok || !data || !len) {
+    napi_throw_type_error(env, "MSM_B200", "expected the Uint8Array view of the wasm memory (memoryBytes)");
+    return NULL;
+  }
+  int rc = pin ? msm_b200_host_register(data, len) : msm_b200_host_unregister(data);
+  if (rc != MSM_OK) napi_throw_error(env, "MSM_B200", msm_b200_global_error());
+  return NULL;
+}
+static napi_value PinMemory(napi_env env, napi_callback_info info) { return pin_or_unpin(env, info, 1); }
+static napi_value UnpinMemory(napi_env env, napi_callback_info info) { return pin_or_unpin(env, info, 0); }
+
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor props[] = {
       {"createContext", NULL, CreateContext, NULL, NULL, NULL, napi_default, NULL},
       {"setBases", NULL, SetBases, NULL, NULL, NULL, napi_default, NULL},
       {"run", NULL, Run, NULL, NULL, NULL, napi_default, NULL},
       {"destroy", NULL, Destroy, NULL, NULL, NULL, napi_default, NULL},
+      {"pinMemory", NULL, PinMemory, NULL, NULL, NULL, napi_default, NULL},
+      {"unpinMemory", NULL, UnpinMemory, NULL, NULL, NULL, napi_default, NULL},
   };
   NAPI_OK(napi_define_properties(env, exports, sizeof props / sizeof props[0], props));
   return exports;

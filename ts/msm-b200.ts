@@ -70,6 +70,14 @@ function makeRunner(ctx: unknown, Field: any, Scalar: any) {
 
 type MsmOptions = { c?: number; basesGeneration?: unknown };
 
+/** Optional: page-lock the two wasm memories of a curve (after they have reached their final size), so that the
+ *  uploads run as asynchronous DMA at PCIe speed.  Returns the function that undoes it. */
+export function pinCurveMemories(Inputs: any): () => void {
+  const views = [Inputs.Field.memoryBytes, Inputs.Scalar.memoryBytes];
+  for (const v of views) addon.pinMemory(v);
+  return () => views.forEach((v) => addon.unpinMemory(v));
+}
+
 /** Weierstraß curves: drop-in for `createMsm(Inputs)` plus `msmProjective`. */
 export function createMsmB200(Inputs: any, curveId: number, devices: number | number[] = 0) {
   const { Field, Scalar, Affine, Projective } = Inputs;
