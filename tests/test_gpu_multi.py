@@ -70,6 +70,13 @@ def test_multi_equals_single_and_port(mz, name):
                     r1 = m.msm(sc, pts, n)
                     assert (r1.x, r1.y, r1.is_zero) == want
                     assert len(m.last_timings()) == len(devices)
+                    # fewer points than devices: most shards are empty
+                    r5 = m.msm(sc[:5 * 32], pts[:5 * 2 * port.nbytes], 5)
+                    with mz.MsmEngine(name) as eng:
+                        s5 = eng.msm(sc[:5 * 32], pts[:5 * 2 * port.nbytes], 5)
+                    assert (r5.x, r5.y, r5.is_zero) == (s5.x, s5.y, s5.is_zero)
+                    r0 = m.msm(b"", b"", 0)
+                    assert r0.is_zero
             finally:
                 os.environ.pop("MSM_B200_GATHER", None)
 

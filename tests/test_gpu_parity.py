@@ -390,3 +390,49 @@ def test_registered_host_memory(mz):
         L.check(L.lib().msm_b200_host_unregister(C.c_void_p(buf.ctypes.data)))
     with pytest.raises(mz.MsmError):
         L.check(L.lib().msm_b200_host_unregister(C.c_void_p(buf.ctypes.data)))  # not registered any more: a code, no crash
+
+
+def test_two_contexts_from_two_host_threads(mz):
+    """Contexts are independent: two of them driven from two host threads at once (what the N-API addon's worker
+    pool does with two curves) give the same points as one after the other."""
+    import threading
+    params = O.BLS12_377
+    n = 1 << 14
+    from oracle.port import Port
+    port = Port("bls12-377")
+    pts = port.random_points(n, 31, 4)
+    scs = [port.random_scalars(n, 40 + i, 4) for i in range(6)]
+    with mz.MsmEngine("bls12-377") as e0:
+        e0.set_bases(pts, n)
+        want = [(r.x, r.y) for r in (e0.run(s, n) for s in scs)]
+    got = {}
+
+    def work(tid, lo):
+        with mz.MsmEngine("bls12-377") as e:
+            e.set_bases(pts, n)
+            for i in range(lo, lo + 3):
+                r = e.run(scs[i], n) if i % 2 else e.msm(scs[i], pts, n)
+                got[i] = (r.x, r.y)
+
+    th = [threading.Thread(target=work, args=(t, 3 * t)) for t in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert [got[i] for i in range(6)] == want
+
+
+def test_workspace_regrows_and_shrinks_across_calls(mz):
+    """One context, many calls of very different sizes and layouts (buffers are grown on demand and reused)."""
+    from oracle.port import Port
+    port = Port("pallas")
+    nmax = 1 << 15
+    pts = port.random_points(nmax, 51, 4)
+    sc = port.random_scalars(nmax, 52, 4)
+    with mz.MsmEngine("pallas") as eng:
+        for n in (100, nmax, 7, 1 << 14, 3000, nmax, 1, 1 << 13):
+            eng.set_bases(pts, n)
+            a = eng.run(sc, n)
+            b = eng.run(sc, n, window_bits=7)
+            assert (a.x, a.y, a.is_zero) == (b.x, b.y, b.is_zero), n
+            assert (a.x, a.y, a.is_zero) == port.msm(sc[:32 * n], port.prepare_points(pts[:64 * n], n, 4), n, 4)[:3], n
