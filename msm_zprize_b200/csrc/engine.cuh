@@ -93,6 +93,7 @@ struct msm_b200_ctx {
   do {                                                                                       \
     cudaError_t e_ = (call);                                                                 \
     if (e_ != cudaSuccess) {                                                                 \
+      cudaGetLastError(); /* a non-sticky error must not surface again in a later, unrelated call */ \
       char buf_[512];                                                                        \
       snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
       if (ctx) ctx->err = buf_;                                                              \
