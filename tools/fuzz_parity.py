@@ -25,7 +25,7 @@ while time.time() < t_end:
     curve = rng.choice(CURVES)
     port, eng = ports[curve], engines[curve]
     te = curve == "ed-on-bls12-377"
-    lg = rng.choice([0, 3, 6, 9, 11, 12, 13, 14, 14, 15, 15, 16])
+    lg = rng.choice([0, 3, 6, 9, 11, 12, 13, 14, 14, 15, 15, 16] + ([17, 17, 18] if os.environ.get("FUZZ_LARGE") else []))
     n = max(1, rng.randrange(1 << lg, (2 << lg)))
     nb = port.nbytes
     pts = bytearray(port.random_points(n, rng.getrandbits(40), threads))
