@@ -48,14 +48,14 @@ _lib = None
 
 EXPORTS = [
     "msm_b200_create", "msm_b200_destroy", "msm_b200_last_error", "msm_b200_global_error",
-    "msm_b200_set_bases", "msm_b200_set_bases_async", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial", "msm_b200_last_timing",
+    "msm_b200_set_bases", "msm_b200_share_bases", "msm_b200_set_bases_async", "msm_b200_run", "msm_b200_msm", "msm_b200_run_partial", "msm_b200_last_timing",
     "msm_b200_partial_bytes", "msm_b200_combine", "msm_b200_random_points",
     "msm_b200_random_scalars", "msm_b200_point_bytes", "msm_b200_scalar_bytes",
     "msm_b200_random_points_at", "msm_b200_random_scalars_at",
     "msm_b200_dev_alloc", "msm_b200_dev_free", "msm_b200_host_alloc_pinned",
     "msm_b200_host_free_pinned", "msm_b200_host_register", "msm_b200_host_unregister", "msm_b200_memcpy_d2h", "msm_b200_memcpy_h2d",
     "msm_b200_multi_create", "msm_b200_multi_destroy", "msm_b200_multi_last_error", "msm_b200_multi_devices",
-    "msm_b200_multi_gather_kind", "msm_b200_multi_shard_range", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_set_bases_sharded",
+    "msm_b200_multi_gather_kind", "msm_b200_multi_shard_range", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_share_bases", "msm_b200_multi_set_bases_sharded",
     "msm_b200_multi_run", "msm_b200_multi_run_sharded", "msm_b200_multi_msm", "msm_b200_multi_last_timings",
 ]
 # include/msm_b200_test.h
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     L.msm_b200_global_error.restype = C.c_char_p
     L.msm_b200_set_bases.argtypes = [vp, vp, sz, ci, ci]
     L.msm_b200_set_bases_async.argtypes = [vp, vp, sz, ci]
+    L.msm_b200_share_bases.argtypes = [vp, vp]
     L.msm_b200_run.argtypes = [vp, vp, sz, ci, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_msm.argtypes = [vp, vp, ci, vp, ci, sz, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_run_partial.argtypes = [vp, vp, sz, ci, ci, ci, ci, vp, C.POINTER(Timing)]
@@ -115,6 +116,7 @@ def lib() -> C.CDLL:
     L.msm_b200_multi_ctx.argtypes = [vp, ci]
     L.msm_b200_multi_ctx.restype = vp
     L.msm_b200_multi_set_bases.argtypes = [vp, vp, sz, ci]
+    L.msm_b200_multi_share_bases.argtypes = [vp, vp]
     L.msm_b200_multi_set_bases_sharded.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), ci]
     L.msm_b200_multi_run.argtypes = [vp, vp, sz, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_multi_run_sharded.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]

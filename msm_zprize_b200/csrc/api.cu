@@ -35,6 +35,8 @@ static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int l
   }
   if (n > ((size_t)1 << 30)) return fail(ctx, MSM_E_INVALID, "too many points (max 2^30)");
   CK(cudaSetDevice(ctx->device));
+  ctx->bases_owner = nullptr;  // own bases from now on
+  ctx->bases_gen++;            // contexts that borrowed the previous set must not read the new one by accident
   const void* d_in = points;
   cudaStream_t main_stream = ctx->stream;
   if (overlapped) {
@@ -69,6 +71,8 @@ static int run_partial_impl(msm_b200_ctx* ctx, const void* scalars, size_t n, in
   if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
   if (layout != MSM_LAYOUT_LIMB29_MONT && layout != MSM_LAYOUT_LE_BYTES) return fail(ctx, MSM_E_INVALID, "bad scalar layout");
   if (n > ctx->n_bases) return fail(ctx, MSM_E_STATE, "more scalars than resident bases (call set_bases first)");
+  if (ctx->bases_owner && ctx->bases_owner->bases_gen != ctx->borrowed_gen)
+    return fail(ctx, MSM_E_STATE, "the shared bases were replaced by their owner (call msm_b200_share_bases again)");
   if (n > 0 && !scalars) return fail(ctx, MSM_E_INVALID, "null scalars");
   const bool te = ctx->curve == MSM_CURVE_ED_ON_BLS12_377;
   if (te && form != MSM_FORM_TE_EXTENDED) return fail(ctx, MSM_E_INVALID, "twisted Edwards curve needs MSM_FORM_TE_EXTENDED");
@@ -278,6 +282,32 @@ int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layo
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return rc;
+}
+
+int msm_b200_share_bases(msm_b200_ctx* ctx, msm_b200_ctx* owner) {
+  if (!ctx || !owner || ctx == owner) return fail(ctx, MSM_E_INVALID, "bad arguments");
+  if (ctx->curve != owner->curve || ctx->device != owner->device)
+    return fail(ctx, MSM_E_INVALID, "shared bases need the same curve and device");
+  if (owner->bases_owner) return fail(ctx, MSM_E_INVALID, "the lender must own its bases");
+  CK(cudaSetDevice(owner->device));
+  // everything queued on both contexts first: the lender's ingest / tables, the borrower's last MSM
+  if (owner->bases_pending) {
+    CK(cudaStreamSynchronize(owner->copy_stream));
+    owner->bases_pending = false;
+  }
+  CK(cudaStreamSynchronize(owner->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->bases_pending) {
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->bases_pending = false;
+  }
+  release(ctx->bases);  // the borrower's own record sets are not needed any more
+  ctx->bases_owner = owner;
+  ctx->borrowed_gen = owner->bases_gen;
+  ctx->n_bases = owner->n_bases;
+  ctx->table_c = owner->table_c;
+  ctx->table_K = owner->table_K;
+  return 0;
 }
 
 int msm_b200_set_bases_async(msm_b200_ctx* ctx, const void* points_host, size_t n, int layout) {

@@ -73,6 +73,11 @@ struct msm_b200_ctx {
   // resident bases
   DevBuf bases;
   size_t n_bases = 0;
+  // bases borrowed from another context of the same device and curve (msm_b200_share_bases): several contexts
+  // can then run MSMs over ONE resident point set at the same time (pipelined MSMs, see bench.py `pipelined`).
+  // `bases_gen` counts this context's set_bases calls; a borrower remembers the lender's value.
+  const msm_b200_ctx* bases_owner = nullptr;
+  unsigned long long bases_gen = 0, borrowed_gen = 0;
   // window tables of the resident bases (shared-bucket mode, see k_build_table): table k = 2^(k * table_c) G
   int table_c = 0, table_K = 0;      // 0: no tables
   bool tables_enabled = true;        // MSM_B200_TABLES=0 disables
@@ -147,6 +152,11 @@ static void release(DevBuf& b) {
   } while (0)
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// the resident record sets this context reads (its own or the lender's)
+static inline const uint4* bases_ptr(const msm_b200_ctx* ctx) {
+  return (const uint4*)(ctx->bases_owner ? ctx->bases_owner->bases.p : ctx->bases.p);
+}
 
 // call before the first kernel that reads ctx->bases
 static int wait_for_bases(msm_b200_ctx* ctx) {
@@ -512,7 +522,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   if (split) {
     LAUNCH(ctx, k_bucket_acc_v<C>, cdiv(V, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
            (const uint32_t*)ctx->po.p + NB, (const uint32_t*)ctx->pairkey[0].p, (const uint32_t*)ctx->ent.p,
-           (const uint4*)ctx->bases.p, (uint32_t)V, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->elem[0].p);
+           bases_ptr(ctx), (uint32_t)V, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->elem[0].p);
     // buckets with many pieces: halving passes; with few: a short serial loop in k_bucket_combine
     const unsigned long long max_pieces = (ctx->h_totals[MAX_ROUNDS + 1] + BUCKET_SPLIT - 1) / BUCKET_SPLIT;
     int serial_max = 1 << 30;
@@ -526,7 +536,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
            (const uint4*)ctx->elem[0].p, (uint32_t)NB, (uint32_t)BUCKET_SPLIT, serial_max, (uint4*)ctx->buckets.p);
   } else {
     LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
-           (const uint32_t*)ctx->ent.p, (const uint4*)ctx->bases.p, (uint32_t)NB, (uint4*)ctx->buckets.p);
+           (const uint32_t*)ctx->ent.p, bases_ptr(ctx), (uint32_t)NB, (uint4*)ctx->buckets.p);
   }
   int h1 = T.mark();
   CK(cudaGetLastError());
@@ -728,7 +738,7 @@ static int run_affine_glv(msm_b200_ctx* ctx, const void* d_scalars, size_t n, in
     a.pairkey = (const uint32_t*)ctx->pairkey[r & 1].p;
     a.pairkey_next = (uint32_t*)ctx->pairkey[(r + 1) & 1].p;
     a.ent = (const uint32_t*)ctx->ent.p;
-    a.bases = (const uint4*)ctx->bases.p;
+    a.bases = bases_ptr(ctx);
     // elements of round r (r >= 1) live in elem[(r-1)&1] with capacity P_r; outputs go to elem[r&1]
     a.in.base = (uint4*)ctx->elem[(r + 1) & 1].p;
     a.in.cap = P;

@@ -310,6 +310,23 @@ int msm_b200_multi_set_bases(msm_b200_multi* m, const void* points_host, size_t 
   return rc;
 }
 
+// msm_b200_share_bases for every device: `m` runs over the bases resident in `owner` (same curve, same devices in
+// the same order), so that several multi contexts can have MSMs in flight over one point set
+int msm_b200_multi_share_bases(msm_b200_multi* m, msm_b200_multi* owner) {
+  if (!m || !owner || m == owner) return mfail(m, MSM_E_INVALID, "bad arguments");
+  if (m->curve != owner->curve || m->devices != owner->devices) return mfail(m, MSM_E_INVALID, "shared bases need the same curve and devices");
+  std::lock_guard<std::mutex> lk(m->call_mutex);
+  std::lock_guard<std::mutex> lk2(owner->call_mutex);
+  for (int g = 0; g < m->n_dev; g++) {
+    int rc = msm_b200_share_bases(m->ctx[g], owner->ctx[g]);
+    if (rc != 0) return mfail(m, rc, m->ctx[g]->err);
+  }
+  m->lo = owner->lo;
+  m->cnt = owner->cnt;
+  m->n_bases = owner->n_bases;
+  return 0;
+}
+
 // bases that already live on the devices (benchmarks: the seeded generators): shard g is `points_dev[g]`,
 // n_per_dev[g] points in device g's memory; the global order is shard 0, shard 1, ...
 int msm_b200_multi_set_bases_sharded(msm_b200_multi* m, const void* const* points_dev, const size_t* n_per_dev, int layout) {

@@ -114,6 +114,12 @@ class MsmEngine:
         self._pending_points = keep
         L.check(self._lib.msm_b200_set_bases_async(self._ctx, ptr, n, layout), self._ctx)
 
+    def share_bases(self, owner: "MsmEngine"):
+        """Run over the bases resident in `owner` (same device and curve) without copying them: several engines, each
+        driven by its own host thread, can then work on independent scalar vectors at the same time."""
+        L.check(self._lib.msm_b200_share_bases(self._ctx, owner._ctx), self._ctx)
+        self._bases_owner = owner  # keep the lender alive
+
     def set_bases_device(self, dev_ptr: int, n: int, layout: int = L.LAYOUT_LE_BYTES):
         L.check(self._lib.msm_b200_set_bases(self._ctx, C.c_void_p(dev_ptr), n, layout, 1), self._ctx)
 
@@ -208,6 +214,55 @@ class MsmEngine:
         return out[: 2 * n * K.value].reshape(2 * n, K.value)
 
 
+class PipelinedMsm:
+    """`depth` engines on one GPU over ONE resident point set (msm_b200_share_bases), each driven by its own host
+    thread: independent MSMs submitted back to back overlap -- the inversions and the bucket reduction of one run
+    beside the rounds of another.  submit() returns a Future of MsmResult; results come back in submission order
+    through map()."""
+
+    def __init__(self, curve: str | int, device: int = 0, depth: int = 2):
+        from concurrent.futures import ThreadPoolExecutor
+        import queue
+        self.engines = [MsmEngine(curve, device=device) for _ in range(depth)]
+        self._free: "queue.Queue[MsmEngine]" = queue.Queue()
+        for e in self.engines:
+            self._free.put(e)
+        self._pool = ThreadPoolExecutor(max_workers=depth)
+
+    def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES, on_device: bool = False):
+        own = self.engines[0]
+        if on_device:
+            own.set_bases_device(int(points), n, layout)
+        else:
+            own.set_bases(points, n, layout)
+        for e in self.engines[1:]:
+            e.share_bases(own)
+
+    def _run(self, scalars, n, kw):
+        e = self._free.get()
+        try:
+            return e.run(scalars, n, **kw)
+        finally:
+            self._free.put(e)
+
+    def submit(self, scalars, n: int, **kw):
+        return self._pool.submit(self._run, scalars, n, kw)
+
+    def map(self, scalar_sets, n: int, **kw):
+        return [f.result() for f in [self.submit(s, n, **kw) for s in scalar_sets]]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for e in reversed(self.engines):  # borrowers first
+            e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 class MultiMsmEngine:
     """Several GPUs behind one call (msm_b200_multi_*): the library shards the points by range, drives every
     device from its own host thread, gathers the partial points (NCCL / peer copies) and adds them on
@@ -259,6 +314,12 @@ class MultiMsmEngine:
     def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
         ptr, keep = _as_buffer(points, n * self.shards[0].point_bytes(layout), "point buffer")
         L.check(self._lib.msm_b200_multi_set_bases(self._m, ptr, n, layout), multi=self._m)
+
+    def share_bases(self, owner: "MultiMsmEngine"):
+        """Run over the bases resident in `owner` (same curve and device list): several multi engines, each driven from
+        its own host thread, can then have MSMs in flight over one point set."""
+        L.check(self._lib.msm_b200_multi_share_bases(self._m, owner._m), multi=self._m)
+        self._bases_owner = owner
 
     def set_bases_sharded(self, dev_ptrs, counts, layout: int = L.LAYOUT_LE_BYTES):
         p = (C.c_void_p * len(dev_ptrs))(*[C.c_void_p(int(x)) for x in dev_ptrs])

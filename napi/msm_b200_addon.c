@@ -12,6 +12,8 @@
  *   setBases(ctx, memoryBytes, byteOffset, n, layout)                -> Promise<void>
  *   run(ctx, memoryBytes, byteOffset, n, layout, form, windowBits)   -> Promise<{x, y, isZero, timing}>
  *       (memoryBytes: the Uint8Array over the wasm memory)
+ *   shareBases(ctx, ownerCtx)   run over the bases resident in another context (same curve and devices): several
+ *       contexts can then have MSMs in flight over one point set (throughput of a stream of MSMs)
  *   destroy(ctx)
  *   pinMemory(memoryBytes) / unpinMemory(memoryBytes)
  *       page-lock the buffer behind a wasm memory (once, after the memory has its final size), so that uploads from
@@ -320,6 +322,22 @@ static napi_value start_job(napi_env env, napi_callback_info info, int is_run) {
 static napi_value SetBases(napi_env env, napi_callback_info info) { return start_job(env, info, 0); }
 static napi_value Run(napi_env env, napi_callback_info info) { return start_job(env, info, 1); }
 
+static napi_value ShareBases(napi_env env, napi_callback_info info) {
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  if (argc < 2) {
+    napi_throw_type_error(env, "MSM_B200", "expected (ctx, ownerCtx)");
+    return NULL;
+  }
+  ctx_box* box = unbox(env, argv[0], 1);
+  if (!box) return NULL;
+  ctx_box* owner = unbox(env, argv[1], 1);
+  if (!owner) return NULL;
+  if (msm_b200_multi_share_bases(box->m, owner->m) != MSM_OK) napi_throw_error(env, "MSM_B200", msm_b200_multi_last_error(box->m));
+  return NULL;
+}
+
 static napi_value pin_or_unpin(napi_env env, napi_callback_info info, int pin) {
   size_t argc = 1;
   napi_value argv[1];
@@ -345,6 +363,7 @@ static napi_value Init(napi_env env, napi_value exports) {
       {"setBases", NULL, SetBases, NULL, NULL, NULL, napi_default, NULL},
       {"run", NULL, Run, NULL, NULL, NULL, napi_default, NULL},
       {"destroy", NULL, Destroy, NULL, NULL, NULL, napi_default, NULL},
+      {"shareBases", NULL, ShareBases, NULL, NULL, NULL, napi_default, NULL},
       {"pinMemory", NULL, PinMemory, NULL, NULL, NULL, napi_default, NULL},
       {"unpinMemory", NULL, UnpinMemory, NULL, NULL, NULL, napi_default, NULL},
   };

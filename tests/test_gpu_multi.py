@@ -109,6 +109,36 @@ def test_multi_sharded_device_inputs(mz):
             assert (r.x, r.y, r.is_zero) == (want.x, want.y, want.is_zero), devices
 
 
+def test_multi_contexts_share_bases(mz):
+    """Two multi contexts over ONE resident point set (msm_b200_multi_share_bases), driven from two host threads."""
+    import threading
+    from oracle.port import Port
+    name, n = "pallas", (1 << 14) + 9
+    port = Port(name)
+    pts = port.random_points(n, 81, 4)
+    scs = [port.random_scalars(n, 90 + i, 4) for i in range(4)]
+    prep = port.prepare_points(pts, n, 4)
+    want = [port.msm(s, prep, n, 4)[:3] for s in scs]
+    for devices in _device_sets()[:2]:
+        with mz.MultiMsmEngine(name, devices) as a, mz.MultiMsmEngine(name, devices) as b:
+            a.set_bases(pts, n)
+            b.share_bases(a)
+            got = [None] * 4
+
+            def work(m, idx):
+                for i in idx:
+                    r = m.run(scs[i], n)
+                    got[i] = (r.x, r.y, r.is_zero)
+
+            th = [threading.Thread(target=work, args=(a, (0, 2))), threading.Thread(target=work, args=(b, (1, 3)))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert got == want, devices
+            b.close()  # the borrower goes first
+
+
 def test_multi_errors_are_codes(mz):
     with pytest.raises(mz.MsmError):
         mz.MultiMsmEngine("bls12-377", [0, 0])  # duplicate device

@@ -436,3 +436,36 @@ def test_workspace_regrows_and_shrinks_across_calls(mz):
             b = eng.run(sc, n, window_bits=7)
             assert (a.x, a.y, a.is_zero) == (b.x, b.y, b.is_zero), n
             assert (a.x, a.y, a.is_zero) == port.msm(sc[:32 * n], port.prepare_points(pts[:64 * n], n, 4), n, 4)[:3], n
+
+
+def test_shared_bases_and_pipelined_msms(mz):
+    """msm_b200_share_bases: a second context runs over the first one's resident bases (no copy), also at the same
+    time from another host thread; the loan ends with the lender's next set_bases (MSM_E_STATE, no stale read)."""
+    from oracle.port import Port
+    from msm_zprize_b200 import _lib as L
+    port = Port("bls12-377")
+    n = (1 << 14) + 11
+    pts = port.random_points(n, 61, 4)
+    scs = [port.random_scalars(n, 70 + i, 4) for i in range(6)]
+    prep = port.prepare_points(pts, n, 4)
+    want = [port.msm(s, prep, n, 4)[:3] for s in scs]
+    with mz.PipelinedMsm("bls12-377", depth=2) as pipe:
+        pipe.set_bases(pts, n)
+        got = pipe.map(scs, n)
+        assert [(r.x, r.y, r.is_zero) for r in got] == want
+        assert all(r.timing["shared_buckets"] == 1 for r in got)
+        owner, borrower = pipe.engines
+        pts2 = port.random_points(n, 62, 4)
+        owner.set_bases(pts2, n)  # the lender replaces its bases: the borrower must refuse, not read the new set
+        with pytest.raises(mz.MsmError) as e:
+            borrower.run(scs[0], n)
+        assert e.value.code == L.E_STATE
+        borrower.share_bases(owner)
+        r = borrower.run(scs[0], n)
+        assert (r.x, r.y, r.is_zero) == port.msm(scs[0], port.prepare_points(pts2, n, 4), n, 4)[:3]
+        borrower.set_bases(pts, n)  # bases of its own again
+        r = borrower.run(scs[1], n)
+        assert (r.x, r.y, r.is_zero) == want[1]
+    with mz.MsmEngine("bls12-377") as a, mz.MsmEngine("pallas") as b:
+        with pytest.raises(mz.MsmError):
+            a.share_bases(b)  # different curve
