@@ -50,21 +50,46 @@ function toLog(timing: Timing, verbose: boolean): any[][] {
  *  on a caller-supplied generation: pass `options.basesGeneration` (any value that changes whenever the
  *  points at `pointPtr` change) to keep the bases resident across calls; WITHOUT it every call uploads the
  *  points again, which is what the reference's msm does (it reads the points on every call). */
-function makeRunner(ctx: unknown, Field: any, Scalar: any) {
+function makeRunner(contexts: unknown[], Field: any, Scalar: any) {
+  // contexts[0] owns the resident bases, the others borrow them (addon.shareBases): with k contexts a caller that
+  // issues several msm() calls without awaiting each (Promise.all) keeps k MSMs in flight on the GPU -- the
+  // inversions and the bucket reduction of one run beside the rounds of another (+29 % MSMs per second at 2^18
+  // points with two contexts, +45 % with four).  A caller that awaits every call, like the reference's drivers,
+  // sees exactly the single-context behaviour.
   let basesKey: string | undefined;
-  let chain: Promise<unknown> = Promise.resolve(); // one call in flight per context (the addon rejects overlap)
-  return function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number, generation?: unknown) {
-    const job = chain.then(async () => {
-      const key = generation === undefined ? undefined : `${String(generation)}:${pointPtr}:${N}`;
-      if (key === undefined || key !== basesKey) {
-        basesKey = undefined;
-        await addon.setBases(ctx, Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
-        basesKey = key;
-      }
+  let basesJob: Promise<unknown> = Promise.resolve(); // uploads are serialised and wait for every running MSM
+  const free = [...contexts];
+  const waiters: ((ctx: unknown) => void)[] = [];
+  const acquire = () => (free.length ? Promise.resolve(free.pop()!) : new Promise<unknown>((r) => waiters.push(r)));
+  const release = (ctx: unknown) => (waiters.length ? waiters.shift()!(ctx) : free.push(ctx));
+  async function withAll<T>(f: () => Promise<T>): Promise<T> {
+    const held = await Promise.all(contexts.map(() => acquire()));
+    try {
+      return await f();
+    } finally {
+      held.forEach(release);
+    }
+  }
+  return async function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number, generation?: unknown) {
+    const key = generation === undefined ? undefined : `${String(generation)}:${pointPtr}:${N}`;
+    if (key === undefined || key !== basesKey) {
+      basesJob = basesJob.then(() =>
+        withAll(async () => {
+          if (key !== undefined && key === basesKey) return; // another call uploaded the same set meanwhile
+          basesKey = undefined;
+          await addon.setBases(contexts[0], Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
+          for (const other of contexts.slice(1)) addon.shareBases(other, contexts[0]);
+          basesKey = key;
+        })
+      );
+      await basesJob;
+    }
+    const ctx = await acquire();
+    try {
       return (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
-    });
-    chain = job.catch(() => undefined);
-    return job;
+    } finally {
+      release(ctx);
+    }
   };
 }
 
@@ -79,13 +104,13 @@ export function pinCurveMemories(Inputs: any): () => void {
 }
 
 /** Weierstraß curves: drop-in for `createMsm(Inputs)` plus `msmProjective`. */
-export function createMsmB200(Inputs: any, curveId: number, devices: number | number[] = 0) {
+export function createMsmB200(Inputs: any, curveId: number, devices: number | number[] = 0, contexts = 1) {
   const { Field, Scalar, Affine, Projective } = Inputs;
   // several devices: ONE msm() call range-shards the points over them inside the library (one host thread per
   // GPU, NCCL gather of the partial points, sum on the first device) -- the shape of the reference's SPMD call
   // over its thread pool (src/threads/threads.ts:354-359, src/msm-batched-affine.ts:294-322)
-  const ctx = addon.createContext(curveId, devices);
-  const run = makeRunner(ctx, Field, Scalar);
+  const ctxs = Array.from({ length: Math.max(1, contexts) }, () => addon.createContext(curveId, devices));
+  const run = makeRunner(ctxs, Field, Scalar);
 
   async function call(scalarPtr: number, pointPtr: number, N: number, verbose: boolean, form: number,
                       { c = 0, basesGeneration }: MsmOptions) {
@@ -107,14 +132,14 @@ export function createMsmB200(Inputs: any, curveId: number, devices: number | nu
     call(scalarPtr, pointPtr, N, false, FORM_PROJECTIVE, options);
   // the engine always applies the safe addition rules (batchAddNew, src/curve-affine.ts:376-458), which agree
   // with the unsafe ones wherever those are defined
-  return { msm, msmUnsafe: msm, msmProjective, destroy: () => addon.destroy(ctx) };
+  return { msm, msmUnsafe: msm, msmProjective, destroy: () => [...ctxs].reverse().forEach((c) => addon.destroy(c)) };
 }
 
 /** Twisted Edwards (ed-on-bls12-377): drop-in for `createMsmBasic(Inputs)` (src/msm-basic.ts:34-43). */
-export function createMsmBasicB200(Inputs: any, devices: number | number[] = 0) {
+export function createMsmBasicB200(Inputs: any, devices: number | number[] = 0, contexts = 1) {
   const { Field, Scalar, Curve } = Inputs;
-  const ctx = addon.createContext(CURVE_ED_ON_BLS12_377, devices);
-  const run = makeRunner(ctx, Field, Scalar);
+  const ctxs = Array.from({ length: Math.max(1, contexts) }, () => addon.createContext(CURVE_ED_ON_BLS12_377, devices));
+  const run = makeRunner(ctxs, Field, Scalar);
 
   async function msm(scalarPtr: number, pointPtr: number, N: number, { c = 0, basesGeneration }: MsmOptions = {}) {
     const result = Field.global.getPointer(Curve.size);
@@ -124,5 +149,5 @@ export function createMsmBasicB200(Inputs: any, devices: number | number[] = 0) 
     Curve.fromBigint(result, { X: x, Y: y, Z: 1n, T: (x * y) % Field.p });
     return { result, log: [] as any[][] };
   }
-  return Object.assign(msm, { destroy: () => addon.destroy(ctx) });
+  return Object.assign(msm, { destroy: () => [...ctxs].reverse().forEach((c) => addon.destroy(c)) });
 }
