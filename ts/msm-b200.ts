@@ -70,23 +70,42 @@ function makeRunner(contexts: unknown[], Field: any, Scalar: any) {
       held.forEach(release);
     }
   }
+  const runOn = async (ctx: unknown, scalarPtr: number, N: number, form: number, c: number) =>
+    (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
+  async function upload(pointPtr: number, N: number) {
+    await addon.setBases(contexts[0], Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
+    for (const other of contexts.slice(1)) addon.shareBases(other, contexts[0]);
+  }
   return async function run(scalarPtr: number, pointPtr: number, N: number, form: number, c: number, generation?: unknown) {
-    const key = generation === undefined ? undefined : `${String(generation)}:${pointPtr}:${N}`;
-    if (key === undefined || key !== basesKey) {
-      basesJob = basesJob.then(() =>
+    if (generation === undefined) {
+      // no residency promise: the points are read on this call, like the reference does -- upload and MSM are one
+      // critical section over all contexts
+      const job = basesJob.then(() =>
         withAll(async () => {
-          if (key !== undefined && key === basesKey) return; // another call uploaded the same set meanwhile
           basesKey = undefined;
-          await addon.setBases(contexts[0], Field.memoryBytes, pointPtr, N, LAYOUT_LIMB29_MONT);
-          for (const other of contexts.slice(1)) addon.shareBases(other, contexts[0]);
+          await upload(pointPtr, N);
+          return runOn(contexts[0], scalarPtr, N, form, c);
+        })
+      );
+      basesJob = job.catch(() => undefined);
+      return job;
+    }
+    const key = `${String(generation)}:${pointPtr}:${N}`;
+    if (key !== basesKey) {
+      const job = basesJob.then(() =>
+        withAll(async () => {
+          if (key === basesKey) return; // another call uploaded the same set meanwhile
+          basesKey = undefined;
+          await upload(pointPtr, N);
           basesKey = key;
         })
       );
-      await basesJob;
+      basesJob = job.catch(() => undefined);
+      await job;
     }
     const ctx = await acquire();
     try {
-      return (await addon.run(ctx, Scalar.memoryBytes, scalarPtr, N, LAYOUT_LIMB29_MONT, form, c)) as AddonResult;
+      return await runOn(ctx, scalarPtr, N, form, c);
     } finally {
       release(ctx);
     }
