@@ -91,23 +91,29 @@ function makeRunner(contexts: unknown[], Field: any, Scalar: any) {
       return job;
     }
     const key = `${String(generation)}:${pointPtr}:${N}`;
-    if (key !== basesKey) {
-      const job = basesJob.then(() =>
-        withAll(async () => {
-          if (key === basesKey) return; // another call uploaded the same set meanwhile
-          basesKey = undefined;
-          await upload(pointPtr, N);
-          basesKey = key;
-        })
-      );
-      basesJob = job.catch(() => undefined);
-      await job;
-    }
-    const ctx = await acquire();
-    try {
-      return await runOn(ctx, scalarPtr, N, form, c);
-    } finally {
-      release(ctx);
+    for (;;) {
+      if (key !== basesKey) {
+        const job = basesJob.then(() =>
+          withAll(async () => {
+            if (key === basesKey) return; // another call uploaded the same set meanwhile
+            basesKey = undefined;
+            await upload(pointPtr, N);
+            basesKey = key;
+          })
+        );
+        basesJob = job.catch(() => undefined);
+        await job;
+      }
+      const ctx = await acquire(); // while a context is held no upload can start (it needs all of them)
+      if (key !== basesKey) {
+        release(ctx); // another point set was uploaded between the check and the acquisition: again
+        continue;
+      }
+      try {
+        return await runOn(ctx, scalarPtr, N, form, c);
+      } finally {
+        release(ctx);
+      }
     }
   };
 }
