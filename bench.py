@@ -388,7 +388,30 @@ def pipelined_block(g, sh, curve, n, steps, warm, h_sc, depth=2):
     ms_host, ok2 = run_all(True)
     for e in engines[1:]:
         e.close()
-    return {"contexts": depth, "ms_per_msm": ms_res, "value": n / (ms_res * 1e-3) / 1e6, "unit": UNIT,
+    # the same through the plain-call pipeline of the C ABI (msm_b200_pipeline_submit / _wait: the lanes' host threads
+    # live inside the library), pinned host scalars
+    capi_ms, ok3 = None, True
+    try:
+        with mz.MsmPipeline(curve, [g.local], depth=depth) as pipe:
+            pipe.set_bases(sh.pts.cpu().numpy(), n)
+            for s in range(0, warm, depth):
+                [pipe.wait(t) for t in [pipe.submit(h_sc[u].array, n) for u in range(s, min(warm, s + depth))]]
+            torch.cuda.synchronize(g.dev)
+            t0 = time.perf_counter()
+            tickets = []
+            res = {}
+            for s in range(warm, total):
+                tickets.append((s, pipe.submit(h_sc[s].array, n)))
+                if len(tickets) >= 2 * depth:  # keep the ticket ring short: collect the oldest
+                    s0, t = tickets.pop(0)
+                    res[s0] = pipe.wait(t)
+            for s0, t in tickets:
+                res[s0] = pipe.wait(t)
+            capi_ms = (time.perf_counter() - t0) * 1e3 / steps
+            ok3 = all((res[s].x, res[s].y) == (want[s].x, want[s].y) for s in want)
+    except Exception as e:
+        capi_ms = repr(e)[:200]
+    return {"contexts": depth, "c_api_e2e_ms_per_msm": capi_ms, "c_api_same_points": ok3, "ms_per_msm": ms_res, "value": n / (ms_res * 1e-3) / 1e6, "unit": UNIT,
             "e2e_ms_per_msm": ms_host, "e2e_value": n / (ms_host * 1e-3) / 1e6, "same_points_as_sequential": ok1 and ok2,
             "what": f"{depth} contexts sharing the resident bases, one host thread each, {steps} MSMs submitted back to back "
                     "(wall clock of the whole run / MSMs, no L2 flush in between); one MSM alone takes longer than in the "
@@ -566,7 +589,7 @@ def main():
     if world == 1:
         try:
             pipelined = pipelined_block(g, sh, curve, n, steps, warm, h_sc, max(2, args.pipeline_depth))
-            if not pipelined["same_points_as_sequential"]:
+            if not (pipelined["same_points_as_sequential"] and pipelined["c_api_same_points"]):
                 ok = False
                 notes.append("pipelined MSMs differ from the sequential ones")
         except Exception as e:  # an extra: must not take the headline line with it

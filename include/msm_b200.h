@@ -235,6 +235,25 @@ int msm_b200_multi_msm(msm_b200_multi* m, const void* scalars_host, int scalar_l
  * call's host clock); this returns every device's own phases of the last call */
 int msm_b200_multi_last_timings(msm_b200_multi* m, msm_b200_timing* per_device, int count);
 
+/* -- several MSMs in flight behind plain calls -------------------------------------------------
+ * `depth` lanes over ONE resident point set (lane 0 owns the bases, the others borrow them, msm_b200_share_bases),
+ * each with a dispatcher thread inside the library: submit() hands a scalar vector to the next lane and returns a
+ * ticket at once, wait() blocks until that MSM is done and its point is in the caller's buffer.  Scalars, `out` and
+ * `timing` must stay valid until wait() has returned for the ticket; at most 4 * depth tickets may be outstanding.
+ * Independent MSMs overlap on the GPU (the inversions and the bucket reduction of one beside the rounds of another):
+ * 2^18 points, four lanes: 1.55 instead of 2.25 ms per MSM.  Each lane is a multi context, so `devices` may list
+ * several GPUs. */
+typedef struct msm_b200_pipeline msm_b200_pipeline;
+int msm_b200_pipeline_create(msm_b200_pipeline** out, int curve, const int* devices, int n_dev, int depth);
+void msm_b200_pipeline_destroy(msm_b200_pipeline* p);
+const char* msm_b200_pipeline_last_error(const msm_b200_pipeline* p);
+int msm_b200_pipeline_depth(const msm_b200_pipeline* p);
+/* waits for the MSMs in flight, then uploads and prepares the points (as msm_b200_multi_set_bases) */
+int msm_b200_pipeline_set_bases(msm_b200_pipeline* p, const void* points_host, size_t n, int layout);
+int msm_b200_pipeline_submit(msm_b200_pipeline* p, const void* scalars_host, size_t n, int scalar_layout, int form, int window_bits,
+                             msm_b200_point* out, msm_b200_timing* timing, int* ticket);
+int msm_b200_pipeline_wait(msm_b200_pipeline* p, int ticket);
+
 #ifdef __cplusplus
 }
 #endif

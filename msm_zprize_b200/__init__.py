@@ -6,9 +6,9 @@ the host-side mirror of the reference's `Parallel` interface (src/parallel.ts) o
 """
 from ._lib import (CURVE_BLS12_377_G1, CURVE_BLS12_381_G1, CURVE_ED_ON_BLS12_377, CURVE_PALLAS, FORM_AFFINE_GLV,
                    FORM_PROJECTIVE, FORM_TE_EXTENDED, LAYOUT_LE_BYTES, LAYOUT_LIMB29_MONT, MsmError)
-from .engine import MsmEngine, MsmResult, MultiMsmEngine, PinnedBuffer, PipelinedMsm
+from .engine import MsmEngine, MsmPipeline, MsmResult, MultiMsmEngine, PinnedBuffer, PipelinedMsm
 from .submission import Submission
 
-__all__ = ["MsmEngine", "MultiMsmEngine", "PipelinedMsm", "MsmResult", "MsmError", "PinnedBuffer", "Submission", "CURVE_BLS12_377_G1", "CURVE_PALLAS",
+__all__ = ["MsmEngine", "MultiMsmEngine", "MsmPipeline", "PipelinedMsm", "MsmResult", "MsmError", "PinnedBuffer", "Submission", "CURVE_BLS12_377_G1", "CURVE_PALLAS",
            "CURVE_ED_ON_BLS12_377", "CURVE_BLS12_381_G1", "FORM_AFFINE_GLV", "FORM_PROJECTIVE", "FORM_TE_EXTENDED",
            "LAYOUT_LE_BYTES", "LAYOUT_LIMB29_MONT"]

@@ -57,6 +57,8 @@ EXPORTS = [
     "msm_b200_multi_create", "msm_b200_multi_destroy", "msm_b200_multi_last_error", "msm_b200_multi_devices",
     "msm_b200_multi_gather_kind", "msm_b200_multi_shard_range", "msm_b200_multi_ctx", "msm_b200_multi_set_bases", "msm_b200_multi_share_bases", "msm_b200_multi_set_bases_sharded",
     "msm_b200_multi_run", "msm_b200_multi_run_sharded", "msm_b200_multi_msm", "msm_b200_multi_last_timings",
+    "msm_b200_pipeline_create", "msm_b200_pipeline_destroy", "msm_b200_pipeline_last_error", "msm_b200_pipeline_depth",
+    "msm_b200_pipeline_set_bases", "msm_b200_pipeline_submit", "msm_b200_pipeline_wait",
 ]
 # include/msm_b200_test.h
 TEST_EXPORTS = ["msm_b200_test_field_op", "msm_b200_test_digits", "msm_b200_microbench"]
@@ -122,6 +124,15 @@ def lib() -> C.CDLL:
     L.msm_b200_multi_run_sharded.argtypes = [vp, C.POINTER(vp), ci, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_multi_msm.argtypes = [vp, vp, ci, vp, ci, sz, ci, ci, C.POINTER(Point), C.POINTER(Timing)]
     L.msm_b200_multi_last_timings.argtypes = [vp, C.POINTER(Timing), ci]
+    L.msm_b200_pipeline_create.argtypes = [C.POINTER(vp), ci, C.POINTER(ci), ci, ci]
+    L.msm_b200_pipeline_destroy.argtypes = [vp]
+    L.msm_b200_pipeline_destroy.restype = None
+    L.msm_b200_pipeline_last_error.argtypes = [vp]
+    L.msm_b200_pipeline_last_error.restype = C.c_char_p
+    L.msm_b200_pipeline_depth.argtypes = [vp]
+    L.msm_b200_pipeline_set_bases.argtypes = [vp, vp, sz, ci]
+    L.msm_b200_pipeline_submit.argtypes = [vp, vp, sz, ci, ci, ci, C.POINTER(Point), C.POINTER(Timing), C.POINTER(ci)]
+    L.msm_b200_pipeline_wait.argtypes = [vp, ci]
     L.msm_b200_test_field_op.argtypes = [ci, ci, ci, vp, vp, vp, sz]
     L.msm_b200_test_digits.argtypes = [vp, vp, sz, ci, vp, C.POINTER(ci)]
     L.msm_b200_microbench.argtypes = [ci, ci, ci, C.POINTER(C.c_double), C.POINTER(C.c_float)]

@@ -407,3 +407,143 @@ int msm_b200_multi_last_timings(msm_b200_multi* m, msm_b200_timing* per_device, 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Several MSMs in flight over one resident point set, behind plain calls (msm_b200_pipeline_*): `depth` lanes,
+// each a multi context of its own (lane 0 owns the bases, the others borrow them) with a dispatcher thread.
+// submit() hands a scalar vector to the next lane and returns a ticket at once; wait() blocks until that MSM is
+// done and its point is in the caller's buffer.  A caller without threads of its own thus gets the overlap of
+// the latency-bound phases of one MSM with the rounds of another (bench.py `pipelined`).
+// ------------------------------------------------------------------------------------------
+struct PipeJob {
+  const void* scalars = nullptr;
+  size_t n = 0;
+  int layout = 0, form = 0, window_bits = 0;
+  msm_b200_point* out = nullptr;
+  msm_b200_timing* tm = nullptr;
+  int rc = 0;
+  bool done = true;
+};
+
+struct msm_b200_pipeline {
+  int depth = 0;
+  std::vector<msm_b200_multi*> lanes;
+  std::vector<DeviceWorker*> dispatch;  // one per lane: runs that lane's MSMs in submission order
+  std::vector<PipeJob> jobs;            // ring of tickets; ticket t lives in slot t % jobs.size()
+  std::mutex m;         // tickets and job states
+  std::mutex submit_m;  // one submitter at a time (a lane's dispatcher takes one job at a time)
+  std::condition_variable cv;
+  long long next_ticket = 0;
+  std::string err;
+};
+
+extern "C" {
+
+int msm_b200_pipeline_create(msm_b200_pipeline** out, int curve, const int* devices, int n_dev, int depth) {
+  if (!out) return mfail(nullptr, MSM_E_INVALID, "null out pointer");
+  *out = nullptr;
+  if (depth < 1 || depth > 16) return mfail(nullptr, MSM_E_INVALID, "pipeline depth out of range [1,16]");
+  msm_b200_pipeline* p = new msm_b200_pipeline();
+  p->depth = depth;
+  for (int l = 0; l < depth; l++) {
+    msm_b200_multi* m = nullptr;
+    int rc = msm_b200_multi_create(&m, curve, devices, n_dev);
+    if (rc != 0) {
+      std::string keep = g_err;
+      msm_b200_pipeline_destroy(p);
+      g_err = keep;
+      return rc;
+    }
+    p->lanes.push_back(m);
+    p->dispatch.push_back(new DeviceWorker());
+    p->dispatch.back()->start();
+  }
+  p->jobs.assign((size_t)depth * 4, PipeJob());
+  *out = p;
+  return 0;
+}
+
+// every submitted MSM has finished
+static void pipeline_drain(msm_b200_pipeline* p) {
+  for (DeviceWorker* w : p->dispatch) w->wait();
+}
+
+void msm_b200_pipeline_destroy(msm_b200_pipeline* p) {
+  if (!p) return;
+  for (DeviceWorker* w : p->dispatch) {
+    w->wait();
+    w->stop();
+    delete w;
+  }
+  for (size_t l = p->lanes.size(); l-- > 0;) msm_b200_multi_destroy(p->lanes[l]);  // the borrowers first
+  delete p;
+}
+
+const char* msm_b200_pipeline_last_error(const msm_b200_pipeline* p) { return p ? p->err.c_str() : g_err.c_str(); }
+int msm_b200_pipeline_depth(const msm_b200_pipeline* p) { return p ? p->depth : 0; }
+
+int msm_b200_pipeline_set_bases(msm_b200_pipeline* p, const void* points_host, size_t n, int layout) {
+  if (!p) return mfail(nullptr, MSM_E_INVALID, "null pipeline");
+  std::lock_guard<std::mutex> submit_lock(p->submit_m);
+  pipeline_drain(p);
+  int rc = msm_b200_multi_set_bases(p->lanes[0], points_host, n, layout);
+  for (int l = 1; l < p->depth && rc == 0; l++) rc = msm_b200_multi_share_bases(p->lanes[l], p->lanes[0]);
+  if (rc != 0) p->err = msm_b200_global_error();
+  return rc;
+}
+
+int msm_b200_pipeline_submit(msm_b200_pipeline* p, const void* scalars_host, size_t n, int scalar_layout, int form, int window_bits,
+                             msm_b200_point* out, msm_b200_timing* timing, int* ticket) {
+  if (!p || !out || !ticket) return mfail(nullptr, MSM_E_INVALID, "bad arguments");
+  std::lock_guard<std::mutex> submit_lock(p->submit_m);
+  long long t;
+  PipeJob* job;
+  {
+    std::unique_lock<std::mutex> lk(p->m);
+    t = p->next_ticket;
+    job = &p->jobs[(size_t)(t % (long long)p->jobs.size())];
+    if (!job->done) {
+      p->err = "too many MSMs in flight without msm_b200_pipeline_wait";
+      g_err = p->err;
+      return MSM_E_STATE;
+    }
+    p->next_ticket++;
+    *job = PipeJob();
+    job->scalars = scalars_host;
+    job->n = n;
+    job->layout = scalar_layout;
+    job->form = form;
+    job->window_bits = window_bits;
+    job->out = out;
+    job->tm = timing;
+    job->done = false;
+  }
+  const int lane = (int)(t % p->depth);
+  DeviceWorker* w = p->dispatch[lane];
+  w->wait();  // the lane's previous MSM (its caller may not have waited for it yet)
+  w->post([p, job, lane] {
+    int rc = msm_b200_multi_run(p->lanes[lane], job->scalars, job->n, job->layout, job->form, job->window_bits, job->out, job->tm);
+    std::lock_guard<std::mutex> lk(p->m);
+    job->rc = rc;
+    if (rc != 0) p->err = msm_b200_multi_last_error(p->lanes[lane]);
+    job->done = true;
+    p->cv.notify_all();
+    return rc;
+  });
+  *ticket = (int)(t & 0x7FFFFFFF);
+  return 0;
+}
+
+int msm_b200_pipeline_wait(msm_b200_pipeline* p, int ticket) {
+  if (!p || ticket < 0) return mfail(nullptr, MSM_E_INVALID, "bad arguments");
+  std::unique_lock<std::mutex> lk(p->m);
+  // tickets are the low 31 bits of the submission count; the slot of the most recent one with these bits
+  long long t = (p->next_ticket & ~0x7FFFFFFFll) | ticket;
+  if (t >= p->next_ticket) t -= 0x80000000ll;
+  if (t < 0 || p->next_ticket - t > (long long)p->jobs.size()) return mfail(nullptr, MSM_E_INVALID, "unknown or expired ticket");
+  PipeJob* job = &p->jobs[(size_t)(t % (long long)p->jobs.size())];
+  p->cv.wait(lk, [job] { return job->done; });
+  return job->rc;
+}
+
+}  // extern "C"

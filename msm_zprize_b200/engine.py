@@ -263,6 +263,67 @@ class PipelinedMsm:
         self.close()
 
 
+class MsmPipeline:
+    """msm_b200_pipeline_*: `depth` lanes over one resident point set behind plain calls -- submit() returns a ticket at
+    once, wait() returns the MsmResult.  The library owns the lanes' dispatcher threads; the caller needs none."""
+
+    def __init__(self, curve: str | int, devices=(0,), depth: int = 4):
+        self.curve = CURVES[curve] if isinstance(curve, str) else int(curve)
+        self._lib = L.lib()
+        self._p = C.c_void_p()
+        devs = list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        L.check(self._lib.msm_b200_pipeline_create(C.byref(self._p), self.curve, arr, len(devs), depth))
+        self.depth = depth
+        self.default_form = L.FORM_TE_EXTENDED if self.curve == L.CURVE_ED_ON_BLS12_377 else L.FORM_AFFINE_GLV
+        self._jobs = {}
+        fb = FIELD_BYTES[self.curve]
+        self._pbytes = {L.LAYOUT_LE_BYTES: 2 * fb}
+
+    def _err(self, rc):
+        if rc != 0:
+            msg = (self._lib.msm_b200_pipeline_last_error(self._p) or b"").decode("utf-8", "replace")
+            raise L.MsmError(rc, msg)
+
+    def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
+        need = n * self._pbytes[layout] if layout in self._pbytes else 0
+        ptr, keep = _as_buffer(points, need, "point buffer")
+        self._err(self._lib.msm_b200_pipeline_set_bases(self._p, ptr, n, layout))
+
+    def submit(self, scalars, n: int, layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None, window_bits: int = 0) -> int:
+        ptr, keep = _as_buffer(scalars, n * (32 if layout == L.LAYOUT_LE_BYTES else 36), "scalar buffer")
+        pt, tm, ticket = L.Point(), L.Timing(), C.c_int()
+        form = self.default_form if form is None else form
+        self._err(self._lib.msm_b200_pipeline_submit(self._p, ptr, n, layout, form, window_bits, C.byref(pt), C.byref(tm),
+                                                     C.byref(ticket)))
+        self._jobs[ticket.value] = (pt, tm, keep)  # buffers stay alive until wait()
+        return ticket.value
+
+    def wait(self, ticket: int) -> MsmResult:
+        pt, tm, _ = self._jobs.pop(ticket)
+        self._err(self._lib.msm_b200_pipeline_wait(self._p, ticket))
+        return MsmResult(int.from_bytes(bytes(pt.x), "little"), int.from_bytes(bytes(pt.y), "little"), bool(pt.is_zero),
+                         tm.as_dict())
+
+    def close(self):
+        if self._p:
+            self._lib.msm_b200_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+            self._jobs.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MultiMsmEngine:
     """Several GPUs behind one call (msm_b200_multi_*): the library shards the points by range, drives every
     device from its own host thread, gathers the partial points (NCCL / peer copies) and adds them on

@@ -139,6 +139,33 @@ def test_multi_contexts_share_bases(mz):
             b.close()  # the borrower goes first
 
 
+def test_pipeline_api_submit_wait(mz):
+    """msm_b200_pipeline_*: plain submit / wait calls, the lanes' threads live inside the library."""
+    from oracle.port import Port
+    name, n = "bls12-377", (1 << 14) + 3
+    port = Port(name)
+    pts = port.random_points(n, 101, 4)
+    scs = [port.random_scalars(n, 110 + i, 4) for i in range(7)]
+    prep = port.prepare_points(pts, n, 4)
+    want = [port.msm(s, prep, n, 4)[:3] for s in scs]
+    for devices in _device_sets()[:2]:
+        with mz.MsmPipeline(name, devices, depth=3) as p:
+            p.set_bases(pts, n)
+            tickets = [p.submit(s, n) for s in scs]  # 7 MSMs over 3 lanes, none awaited in between
+            got = [p.wait(t) for t in tickets]
+            assert [(r.x, r.y, r.is_zero) for r in got] == want, devices
+            assert all(r.timing["shared_buckets"] == 1 for r in got)
+            # new bases while nothing is in flight; a short scalar buffer is refused before the call
+            pts2 = port.random_points(n, 102, 4)
+            p.set_bases(pts2, n)
+            r = p.wait(p.submit(scs[0], n))
+            assert (r.x, r.y, r.is_zero) == port.msm(scs[0], port.prepare_points(pts2, n, 4), n, 4)[:3]
+            with pytest.raises(mz.MsmError):
+                p.submit(bytes(10), n)
+    with pytest.raises(mz.MsmError):
+        mz.MsmPipeline(name, [0], depth=0)
+
+
 def test_multi_errors_are_codes(mz):
     with pytest.raises(mz.MsmError):
         mz.MultiMsmEngine("bls12-377", [0, 0])  # duplicate device
