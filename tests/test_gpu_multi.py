@@ -164,6 +164,14 @@ def test_pipeline_api_submit_wait(mz):
                 p.submit(bytes(10), n)
     with pytest.raises(mz.MsmError):
         mz.MsmPipeline(name, [0], depth=0)
+    with mz.MsmPipeline(name, [0], depth=2) as p:
+        t = p.submit(scs[0], n)  # no bases yet: the job fails with a code, delivered by wait()
+        with pytest.raises(mz.MsmError):
+            p.wait(t)
+        p.set_bases(pts, n)  # and the pipeline is usable afterwards
+        r = p.wait(p.submit(scs[1], n))
+        assert (r.x, r.y, r.is_zero) == want[1]
+        p.submit(scs[2], n)  # left in flight: destroy waits for it
 
 
 def test_multi_errors_are_codes(mz):
