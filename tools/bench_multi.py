@@ -20,6 +20,7 @@ ap.add_argument("--total-log2n", type=int, default=22)
 ap.add_argument("--devices", default="1,2")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--depth", type=int, default=0, help="> 0: also time msm_b200_pipeline_* with that many lanes (host scalars)")
 args = ap.parse_args()
 
 n = 1 << args.total_log2n
@@ -67,4 +68,28 @@ for G in [int(x) for x in args.devices.split(",")]:
                           "same_point_as_first": (res.x, res.y) == ref,
                           "per_device_ms": [round(t["digits_ms"] + t["sort_ms"] + t["accumulate_ms"] + t["reduce_ms"], 3)
                                             for t in m.last_timings()]}), flush=True)
+        if args.depth > 0:
+            # several sharded MSMs in flight: every lane is a multi context over the same devices with its own NCCL
+            # communicators; host scalars, plain submit / wait calls
+            pts_host = b"".join(bytes(e.d2h(pp[g], cnt[g] * pb)) for g, e in enumerate(m.shards))
+            with mz.MsmPipeline(args.curve, list(range(G)), depth=args.depth) as pipe:
+                pipe.set_bases(pts_host, n)
+                for _ in range(args.warmup):
+                    pipe.wait(pipe.submit(h.array, n))
+                t0 = time.perf_counter()
+                tickets = [pipe.submit(h.array, n) for _ in range(min(args.steps, 2 * args.depth))]
+                done = 0
+                total = args.steps
+                submitted = len(tickets)
+                last = None
+                while tickets:
+                    last = pipe.wait(tickets.pop(0))
+                    done += 1
+                    if submitted < total:
+                        tickets.append(pipe.submit(h.array, n))
+                        submitted += 1
+                ms = (time.perf_counter() - t0) * 1e3 / total
+            print(json.dumps({"curve": args.curve, "total_log2n": args.total_log2n, "devices": G, "pipeline_depth": args.depth,
+                              "host_scalars_ms_per_msm": round(ms, 3), "mpoints_s": round(n / ms / 1e3, 1),
+                              "same_point": (last.x, last.y) == (res.x, res.y)}), flush=True)
         h.free()
