@@ -501,6 +501,7 @@ int msm_b200_pipeline_submit(msm_b200_pipeline* p, const void* scalars_host, siz
   {
     std::unique_lock<std::mutex> lk(p->m);
     t = p->next_ticket;
+    if (t >= 0x7FFFFFFFll) return mfail(nullptr, MSM_E_STATE, "ticket counter exhausted: create a new pipeline");
     job = &p->jobs[(size_t)(t % (long long)p->jobs.size())];
     if (!job->done) {
       p->err = "too many MSMs in flight without msm_b200_pipeline_wait";
@@ -530,17 +531,16 @@ int msm_b200_pipeline_submit(msm_b200_pipeline* p, const void* scalars_host, siz
     p->cv.notify_all();
     return rc;
   });
-  *ticket = (int)(t & 0x7FFFFFFF);
+  *ticket = (int)t;
   return 0;
 }
 
 int msm_b200_pipeline_wait(msm_b200_pipeline* p, int ticket) {
   if (!p || ticket < 0) return mfail(nullptr, MSM_E_INVALID, "bad arguments");
   std::unique_lock<std::mutex> lk(p->m);
-  // tickets are the low 31 bits of the submission count; the slot of the most recent one with these bits
-  long long t = (p->next_ticket & ~0x7FFFFFFFll) | ticket;
-  if (t >= p->next_ticket) t -= 0x80000000ll;
-  if (t < 0 || p->next_ticket - t > (long long)p->jobs.size()) return mfail(nullptr, MSM_E_INVALID, "unknown or expired ticket");
+  const long long t = ticket;
+  if (t >= p->next_ticket || p->next_ticket - t > (long long)p->jobs.size())
+    return mfail(nullptr, MSM_E_INVALID, "unknown or expired ticket");
   PipeJob* job = &p->jobs[(size_t)(t % (long long)p->jobs.size())];
   p->cv.wait(lk, [job] { return job->done; });
   return job->rc;
