@@ -278,7 +278,9 @@ class MsmPipeline:
         self.default_form = L.FORM_TE_EXTENDED if self.curve == L.CURVE_ED_ON_BLS12_377 else L.FORM_AFFINE_GLV
         self._jobs = {}
         fb = FIELD_BYTES[self.curve]
-        self._pbytes = {L.LAYOUT_LE_BYTES: 2 * fb}
+        n29 = 14 if fb == 48 else 9  # 29-bit limbs per field element (src/bigint/field-util.ts:18-42)
+        limb29 = 4 * 4 * n29 if self.curve == L.CURVE_ED_ON_BLS12_377 else 2 * 4 * n29 + 4
+        self._pbytes = {L.LAYOUT_LE_BYTES: 2 * fb, L.LAYOUT_LIMB29_MONT: limb29}
 
     def _err(self, rc):
         if rc != 0:
@@ -286,8 +288,7 @@ class MsmPipeline:
             raise L.MsmError(rc, msg)
 
     def set_bases(self, points, n: int, layout: int = L.LAYOUT_LE_BYTES):
-        need = n * self._pbytes[layout] if layout in self._pbytes else 0
-        ptr, keep = _as_buffer(points, need, "point buffer")
+        ptr, keep = _as_buffer(points, n * self._pbytes.get(layout, 0), "point buffer")
         self._err(self._lib.msm_b200_pipeline_set_bases(self._p, ptr, n, layout))
 
     def submit(self, scalars, n: int, layout: int = L.LAYOUT_LE_BYTES, form: Optional[int] = None, window_bits: int = 0) -> int:
