@@ -126,7 +126,8 @@ int msm_b200_set_bases(msm_b200_ctx* ctx, const void* points, size_t n, int layo
  * (inversions, bucket reduction) overlap the throughput-bound rounds of another (bench.py `pipelined`: +32 %
  * MSMs per second at 2^18 points with two contexts).  The reference has one MSM in flight per thread pool.
  * The loan ends when `ctx` gets bases of its own; after `owner` replaces ITS bases, runs on `ctx` fail with
- * MSM_E_STATE until msm_b200_share_bases is called again.  `owner` must outlive the loan. */
+ * MSM_E_STATE until msm_b200_share_bases is called again; destroying `owner` ends the loan the same way (the borrower
+ * is left without bases).  Not to be called while either context has an MSM running on another thread. */
 int msm_b200_share_bases(msm_b200_ctx* ctx, msm_b200_ctx* owner);
 /* Same for host points, without waiting: the copy and the ingest kernel are queued on the context's copy
  * stream and the next run / run_partial waits for them only where it first reads a base point, i.e. behind its

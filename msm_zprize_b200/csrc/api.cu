@@ -21,6 +21,14 @@ static const CurveOps* ops_of(int curve) {
   return nullptr;
 }
 
+// ends a loan of resident bases (msm_b200_share_bases), if there is one
+static void drop_borrowed_bases(msm_b200_ctx* ctx) {
+  if (!ctx->bases_owner) return;
+  std::vector<msm_b200_ctx*>& v = ctx->bases_owner->borrowers;
+  v.erase(std::remove(v.begin(), v.end(), ctx), v.end());
+  ctx->bases_owner = nullptr;
+}
+
 static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int layout, int on_device,
                           bool overlapped = false) {
   if (!ctx) return fail(nullptr, MSM_E_INVALID, "null context");
@@ -35,7 +43,7 @@ static int set_bases_impl(msm_b200_ctx* ctx, const void* points, size_t n, int l
   }
   if (n > ((size_t)1 << 30)) return fail(ctx, MSM_E_INVALID, "too many points (max 2^30)");
   CK(cudaSetDevice(ctx->device));
-  ctx->bases_owner = nullptr;  // own bases from now on
+  drop_borrowed_bases(ctx);    // own bases from now on
   ctx->bases_gen++;            // contexts that borrowed the previous set must not read the new one by accident
   const void* d_in = points;
   cudaStream_t main_stream = ctx->stream;
@@ -255,6 +263,14 @@ void msm_b200_destroy(msm_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  drop_borrowed_bases(ctx);
+  for (msm_b200_ctx* b : ctx->borrowers) {  // the loans end here: a later run on a borrower fails with MSM_E_STATE
+    cudaStreamSynchronize(b->stream);
+    b->bases_owner = nullptr;
+    b->n_bases = 0;
+    b->table_c = b->table_K = 0;
+  }
+  ctx->borrowers.clear();
   DevBuf* all[] = {&ctx->bases, &ctx->raw_points, &ctx->raw_scalars, &ctx->hs, &ctx->cnt, &ctx->cntk, &ctx->cursor, &ctx->po,
                    &ctx->totals, &ctx->ent, &ctx->pairkey[0], &ctx->pairkey[1], &ctx->elem[0], &ctx->elem[1],
                    &ctx->prefix, &ctx->red[0], &ctx->red[1], &ctx->partial, &ctx->result, &ctx->buckets, &ctx->rp_tables, &ctx->fin, &ctx->others, &ctx->tilesum};
@@ -302,6 +318,8 @@ int msm_b200_share_bases(msm_b200_ctx* ctx, msm_b200_ctx* owner) {
     ctx->bases_pending = false;
   }
   release(ctx->bases);  // the borrower's own record sets are not needed any more
+  drop_borrowed_bases(ctx);
+  owner->borrowers.push_back(ctx);
   ctx->bases_owner = owner;
   ctx->borrowed_gen = owner->bases_gen;
   ctx->n_bases = owner->n_bases;

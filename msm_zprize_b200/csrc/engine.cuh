@@ -76,8 +76,9 @@ struct msm_b200_ctx {
   // bases borrowed from another context of the same device and curve (msm_b200_share_bases): several contexts
   // can then run MSMs over ONE resident point set at the same time (pipelined MSMs, see bench.py `pipelined`).
   // `bases_gen` counts this context's set_bases calls; a borrower remembers the lender's value.
-  const msm_b200_ctx* bases_owner = nullptr;
+  msm_b200_ctx* bases_owner = nullptr;
   unsigned long long bases_gen = 0, borrowed_gen = 0;
+  std::vector<msm_b200_ctx*> borrowers;  // contexts that read this context's bases (told when it is destroyed)
   // window tables of the resident bases (shared-bucket mode, see k_build_table): table k = 2^(k * table_c) G
   int table_c = 0, table_K = 0;      // 0: no tables
   bool tables_enabled = true;        // MSM_B200_TABLES=0 disables

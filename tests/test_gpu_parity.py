@@ -469,3 +469,15 @@ def test_shared_bases_and_pipelined_msms(mz):
     with mz.MsmEngine("bls12-377") as a, mz.MsmEngine("pallas") as b:
         with pytest.raises(mz.MsmError):
             a.share_bases(b)  # different curve
+    # the lender is destroyed first: the borrower is left without bases (a code, no dangling read)
+    lender, borrower = mz.MsmEngine("bls12-377"), mz.MsmEngine("bls12-377")
+    lender.set_bases(pts, n)
+    borrower.share_bases(lender)
+    lender.close()
+    with pytest.raises(mz.MsmError) as e:
+        borrower.run(scs[0], n)
+    assert e.value.code == L.E_STATE
+    borrower.set_bases(pts, n)
+    r = borrower.run(scs[0], n)
+    assert (r.x, r.y, r.is_zero) == want[0]
+    borrower.close()
