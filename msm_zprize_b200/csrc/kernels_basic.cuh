@@ -115,10 +115,25 @@ __global__ void __launch_bounds__(128) k_bucket_acc(const uint32_t* __restrict__
   typename C::Acc acc = C::zero();
   uint32_t n = cnt[b];
   const uint32_t* e = ent + 2 * (size_t)po0[b];
+  if constexpr (C::BASE_STRIDE == 1) {  // twisted Edwards: fetch the next cached point while adding the current one
+    if (n) {
+      uint32_t en = e[0];
+      typename C::Base cur = C::ld_base(bases, ent_index(en));
 #pragma unroll 1
-  for (uint32_t j = 0; j < n; j++) {
-    uint32_t en = e[j];
-    acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
+      for (uint32_t j = 0; j < n; j++) {
+        const uint32_t en_next = (j + 1 < n) ? e[j + 1] : en;
+        const typename C::Base nxt = C::ld_base(bases, ent_index(en_next));
+        acc = C::add_cached(acc, cur, ent_neg(en));
+        cur = nxt;
+        en = en_next;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (uint32_t j = 0; j < n; j++) {
+      uint32_t en = e[j];
+      acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
+    }
   }
   C::st(buckets + (size_t)b * (C::ACC_FE * C::F::N / 4), acc);
 }
@@ -138,10 +153,26 @@ __global__ void __launch_bounds__(128) k_bucket_acc_v(const uint32_t* __restrict
   uint32_t hi = min(cnt[b], lo + split);
   typename C::Acc acc = C::zero();
   const uint32_t* e = ent + 2 * (size_t)po0[b];
+  if constexpr (C::BASE_STRIDE == 1) {
+    // twisted Edwards: the next cached point is fetched while the current one is added (random 96-byte gathers)
+    if (lo < hi) {
+      uint32_t en = e[lo];
+      typename C::Base cur = C::ld_base(bases, ent_index(en));
 #pragma unroll 1
-  for (uint32_t j = lo; j < hi; j++) {
-    uint32_t en = e[j];
-    acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
+      for (uint32_t j = lo; j < hi; j++) {
+        const uint32_t en_next = (j + 1 < hi) ? e[j + 1] : en;
+        const typename C::Base nxt = C::ld_base(bases, ent_index(en_next));
+        acc = C::add_cached(acc, cur, ent_neg(en));
+        cur = nxt;
+        en = en_next;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (uint32_t j = lo; j < hi; j++) {
+      uint32_t en = e[j];
+      acc = C::add_base(acc, bases, ent_index(en), ent_neg(en));
+    }
   }
   C::st(vacc + (size_t)v * (C::ACC_FE * C::F::N / 4), acc);
 }

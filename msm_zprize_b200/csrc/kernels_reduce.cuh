@@ -269,13 +269,19 @@ struct TeCurve {
     return r;
   }
   __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
+    return ext_add_niels<F>(a, ld_base(bases, idx), neg);
+  }
+  // the cached base point on its own, so that a loop can fetch the next one while it adds the current one
+  typedef Niels<F> Base;
+  __device__ static Base ld_base(const uint4* __restrict__ bases, uint32_t idx) {
     const uint4* p = bases + (size_t)idx * (3 * F::N / 4);
     Niels<F> Q;
     Q.yp = ld_aos<F>(p);
     Q.ym = ld_aos<F>(p + F::N / 4);
     Q.kt = ld_aos<F>(p + 2 * F::N / 4);
-    return ext_add_niels<F>(a, Q, neg);
+    return Q;
   }
+  __device__ static Acc add_cached(const Acc& a, const Base& Q, bool neg) { return ext_add_niels<F>(a, Q, neg); }
   // quad-cooperative doubling (dedicated a = -1 formula dbl-2008-hwcd: 4M + 4S in 2 layers; the
   // reference doubles with the unified addition, src/curve-twisted-edwards.ts:215-227 -- same point)
   __device__ static Acc dblq(const Acc& P) { return dbl_quad(P); }
