@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) k_bucket_acc(const uint32_t* __restrict__
   typename C::Acc acc = C::zero();
   uint32_t n = cnt[b];
   const uint32_t* e = ent + 2 * (size_t)po0[b];
-  if constexpr (C::BASE_STRIDE == 1) {  // twisted Edwards: fetch the next cached point while adding the current one
+  if constexpr (C::PREFETCH_BASE) {  // fetch the next base point while adding the current one
     if (n) {
       uint32_t en = e[0];
       typename C::Base cur = C::ld_base(bases, ent_index(en));
@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(128) k_bucket_acc_v(const uint32_t* __restrict
   uint32_t hi = min(cnt[b], lo + split);
   typename C::Acc acc = C::zero();
   const uint32_t* e = ent + 2 * (size_t)po0[b];
-  if constexpr (C::BASE_STRIDE == 1) {
-    // twisted Edwards: the next cached point is fetched while the current one is added (random 96-byte gathers)
+  if constexpr (C::PREFETCH_BASE) {
+    // the next base point is fetched while the current one is added (random 96-byte gathers)
     if (lo < hi) {
       uint32_t en = e[lo];
       typename C::Base cur = C::ld_base(bases, ent_index(en));

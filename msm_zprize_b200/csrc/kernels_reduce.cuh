@@ -76,6 +76,9 @@ struct WeierCurve {
   static constexpr int ACC_FE = 3;   // field elements per accumulator
   static constexpr int BASE_FE = 2;  // field elements per cached base point (x | y)
   static constexpr int BASE_STRIDE = 2;  // records per input point in ctx->bases (G, endo G)
+  // generic bucket method (kernels_basic.cuh): fetching the next point ahead costs 24 more registers here and loses
+  // (msmProjective 2^22: 43.0 -> 46.1 ms); the twisted-Edwards kernels (8 limbs) gain from it
+  static constexpr bool PREFETCH_BASE = false;
   // QUAD_LAZY (BLS12-377): accumulators held in registers have coordinates < 2p and all additions below are
   // the unreduced variants (ec.cuh proj_*_nr); memory always holds canonical values (st canonicalises).
   __device__ static Acc zero() { return proj_zero<F>(); }
@@ -112,10 +115,18 @@ struct WeierCurve {
   }
   // acc +/- base point `idx` (src/curve-projective.ts addMixed / subMixed)
   __device__ static Acc add_base(const Acc& a, const uint4* __restrict__ bases, uint32_t idx, bool neg) {
+    return add_cached(a, ld_base(bases, idx), neg);
+  }
+  // the base point on its own, so that a loop can fetch the next one while it adds the current one
+  typedef Aff<F> Base;
+  __device__ static Base ld_base(const uint4* __restrict__ bases, uint32_t idx) {
     const uint4* p = bases + (size_t)idx * BASE_STRIDE * (2 * F::N / 4);
     Aff<F> Q;
     Q.x = ld_aos<F>(p);
     Q.y = ld_aos<F>(p + F::N / 4);
+    return Q;
+  }
+  __device__ static Acc add_cached(const Acc& a, Base Q, bool neg) {
     if (aff_is_inf(Q)) return a;
     if (neg) Q.y = fe_neg(Q.y);
     if constexpr (F::LAZY && B3_ == 3) return proj_add_mixed_nr<F>(a, Q);
@@ -240,6 +251,7 @@ struct TeCurve {
   static constexpr int ACC_FE = 4;
   static constexpr int BASE_FE = 3;  // (y+x | y-x | 2d*x*y)
   static constexpr int BASE_STRIDE = 1;
+  static constexpr bool PREFETCH_BASE = true;
   __device__ static Acc zero() { return ext_zero<F>(); }
   __device__ static Acc add(const Acc& a, const Acc& b) { return ext_add<F>(a, b); }
   __device__ static Acc dbl(const Acc& a) { return ext_dbl<F>(a); }
