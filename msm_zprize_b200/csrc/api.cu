@@ -225,6 +225,7 @@ int msm_b200_create(msm_b200_ctx** out, int curve, int device, void* stream) {
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_GB")) ctx->reduce_warp_gb = std::min(std::max(1, atoi(e)), 5);
   if (const char* e = getenv("MSM_B200_REDUCE_Q0")) ctx->reduce_quad0 = atoi(e) != 0;
   if (const char* e = getenv("MSM_B200_TABLES")) ctx->tables_enabled = atoi(e) != 0;
+  if (const char* e = getenv("MSM_B200_BUCKET_SPLIT")) ctx->bucket_split = std::min(std::max(0, atoi(e)), 1 << 20);
   if (const char* e = getenv("MSM_B200_TABLE_WINDOW")) ctx->table_window = std::min(std::max(0, atoi(e)), 24);
   if (const char* e = getenv("MSM_B200_TABLE_MAX_LOG2N")) ctx->table_max_log2n = std::min(std::max(0, atoi(e)), 26);
   if (const char* e = getenv("MSM_B200_REDUCE_WARP_MIN")) ctx->reduce_warp_min = (size_t)std::max(1ll, atoll(e));

@@ -85,6 +85,7 @@ struct msm_b200_ctx {
   int table_max_log2n = 25;          // largest point set that gets tables (MSM_B200_TABLE_MAX_LOG2N): 2^26 points
                                      // with 6 record sets + the workspace of the rounds exceed 180 GB
   int table_window = 0;              // MSM_B200_TABLE_WINDOW: forces the tables' window size (tuning)
+  int bucket_split = 0;              // MSM_B200_BUCKET_SPLIT: entries per virtual bucket of the generic bucket method (0 = by size)
   // workspace
   DevBuf raw_points, raw_scalars, hs, cnt, cntk, cursor, po, totals, ent, pairkey[2], elem[2], prefix;
   DevBuf lvl_pre[8], lvl_tot[8], red[2], partial, result, buckets, rp_tables, fin, others, tilesum;
@@ -501,7 +502,19 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   }
   int e1 = T.mark();
   CK(cudaMemsetAsync(ctx->totals.p, 0, N_TOTALS * 8, ctx->stream));
-  RET_IF(launch_scan(ctx, NB, 2, BUCKET_SPLIT));  // po[0]: padded entry offsets, po[1]: virtual-bucket offsets
+  // entries per virtual bucket: 128 when there are plenty of entries; fewer for smaller inputs, so that the accumulation
+  // still runs on ~2^19 threads (each thread is one serial chain of additions)
+  // (measured, tools/perf_sweep.py with MSM_B200_BUCKET_SPLIT: ed-on-bls12-377 2^16 0.73 -> 0.54 ms with 16, 2^18 1.34 ->
+  // 1.04 ms with 32, 2^22 9.0 -> 8.5 ms with 64, 2^24 best with 128; the 12-limb projective form, few warps per SM at
+  // 178 registers, wants more threads still: msmProjective 2^22 43.0 -> 36.2 ms with 32)
+  uint32_t vsplit = ctx->bucket_split > 0 ? (uint32_t)ctx->bucket_split : (uint32_t)BUCKET_SPLIT;
+  if (ctx->bucket_split <= 0) {
+    const unsigned long long entries = (unsigned long long)n * K;
+    while (vsplit > 32 && entries / vsplit < (1ull << 19)) vsplit >>= 1;
+    if (F::N > 8 && vsplit > 32) vsplit = 32;
+    if (entries < (1ull << 21)) vsplit = 16;
+  }
+  RET_IF(launch_scan(ctx, NB, 2, vsplit));  // po[0]: padded entry offsets, po[1]: virtual-bucket offsets
   CK(cudaMemcpyAsync(ctx->h_totals, ctx->totals.p, N_TOTALS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t P0 = ctx->h_totals[0];
@@ -512,7 +525,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   RET_IF(ensure(ctx, ctx->buckets, NB * C::ACC_FE * FE));
   RET_IF(wait_for_bases(ctx));
   const size_t V = ctx->h_totals[1];
-  const bool split = ctx->h_totals[MAX_ROUNDS + 1] > (unsigned long long)BUCKET_SPLIT;
+  const bool split = ctx->h_totals[MAX_ROUNDS + 1] > (unsigned long long)vsplit;
   if (split) {
     RET_IF(ensure(ctx, ctx->pairkey[0], (V + 1) * 4));
     RET_IF(ensure(ctx, ctx->elem[0], (V + 1) * C::ACC_FE * FE));
@@ -523,9 +536,9 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
   if (split) {
     LAUNCH(ctx, k_bucket_acc_v<C>, cdiv(V, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
            (const uint32_t*)ctx->po.p + NB, (const uint32_t*)ctx->pairkey[0].p, (const uint32_t*)ctx->ent.p,
-           bases_ptr(ctx), (uint32_t)V, (uint32_t)BUCKET_SPLIT, (uint4*)ctx->elem[0].p);
+           bases_ptr(ctx), (uint32_t)V, vsplit, (uint4*)ctx->elem[0].p);
     // buckets with many pieces: halving passes; with few: a short serial loop in k_bucket_combine
-    const unsigned long long max_pieces = (ctx->h_totals[MAX_ROUNDS + 1] + BUCKET_SPLIT - 1) / BUCKET_SPLIT;
+    const unsigned long long max_pieces = (ctx->h_totals[MAX_ROUNDS + 1] + vsplit - 1) / vsplit;
     int serial_max = 1 << 30;
     if (max_pieces > 16) {
       serial_max = 0;  // every multi-piece bucket goes through the tree
@@ -534,7 +547,7 @@ static int run_bucket_basic(msm_b200_ctx* ctx, const void* d_scalars, size_t n, 
                (const uint32_t*)ctx->pairkey[0].p, (uint4*)ctx->elem[0].p, (uint32_t)V, (uint32_t)V, p);
     }
     LAUNCH(ctx, k_bucket_combine<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p + NB,
-           (const uint4*)ctx->elem[0].p, (uint32_t)NB, (uint32_t)BUCKET_SPLIT, serial_max, (uint4*)ctx->buckets.p);
+           (const uint4*)ctx->elem[0].p, (uint32_t)NB, vsplit, serial_max, (uint4*)ctx->buckets.p);
   } else {
     LAUNCH(ctx, k_bucket_acc<C>, cdiv(NB, 128), 128, (const uint32_t*)ctx->cnt.p, (const uint32_t*)ctx->po.p,
            (const uint32_t*)ctx->ent.p, bases_ptr(ctx), (uint32_t)NB, (uint4*)ctx->buckets.p);
