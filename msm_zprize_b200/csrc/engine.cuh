@@ -277,7 +277,9 @@ static int glv_table_window(const msm_b200_ctx* ctx, size_t n) {
   int lg = ceil_log2_sz(n);
   // BLS12-377: 2^21..2^23 -6 %, 2^24 -11 % against no tables; with 8-limb fields the scatter into 2^21 buckets
   // costs more than the sixth window saves
-  return (lg >= 24 && field_is_large(ctx->curve)) ? 22 : (lg >= 21 ? 19 : 16);
+  // (Pallas: 19 only pays from 2^22 points: 2^21 6.22 (c = 16) / 6.26 ms (19), 2^23 21.6 / 21.1 ms)
+  if (!field_is_large(ctx->curve)) return lg >= 22 ? 19 : 16;
+  return lg >= 24 ? 22 : (lg >= 21 ? 19 : 16);
 }
 
 // `tables`: also build the window tables 2^(kc) G (resident bases only; the one-shot call passes false -- the
